@@ -1,0 +1,169 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding for oracle/liboracle.so (CPU restatement of the reference).  May be imported
+only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_cell_noise.restype = C.c_double
+        _LIB.orc_cell_noise.argtypes = [C.c_double]
+        _LIB.orc_percentile.restype = C.c_double
+    return _LIB
+
+
+def _opt(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def rng(seed, n):
+    out = np.empty(n, np.float64)
+    lib().orc_rng(C.c_double(seed), C.c_int(n), _p(out, C.c_double))
+    return out
+
+
+def simplex_perm(seed):
+    perm = np.empty(512, np.uint8)
+    pm12 = np.empty(512, np.uint8)
+    lib().orc_simplex_perm(C.c_double(seed), _p(perm, C.c_uint8), _p(pm12, C.c_uint8))
+    return perm, pm12
+
+
+def noise(seed, kind, xyz, octaves=5, persistence=2.0 / 3):
+    xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+    out = np.empty(xyz.shape[0], np.float64)
+    k = {"noise3D": 0, "fbm": 1, "ridgedFbm": 2}[kind]
+    lib().orc_noise(C.c_double(seed), C.c_int(k), C.c_int(xyz.shape[0]), _p(xyz, C.c_double),
+                    C.c_int(octaves), C.c_double(persistence), _p(out, C.c_double))
+    return out
+
+
+def cell_noise(r):
+    return lib().orc_cell_noise(float(r))
+
+
+_DET = {"exp": 0, "log": 1, "pow": 2, "atan": 3, "asin": 4, "atan2": 5, "sin": 6, "cos": 7, "tanh": 8}
+
+
+def detmath(kind, x, y=None):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros_like(x) if y is None else np.ascontiguousarray(y, np.float64)
+    out = np.empty_like(x)
+    lib().orc_detmath(C.c_int(_DET[kind]), C.c_int(x.size), _p(x, C.c_double), _p(y, C.c_double),
+                      _p(out, C.c_double))
+    return out
+
+
+def fibonacci_sphere(n, jitter, seed):
+    """js/sphere-mesh.js:9-37 + pole (0,0,1) appended (js/sphere-mesh.js:179-181)."""
+    out = np.zeros(3 * (n + 1), np.float32)
+    lib().orc_fibonacci_sphere(C.c_int(n), C.c_double(jitter), C.c_double(seed), _p(out, C.c_float))
+    out[3 * n:] = (0, 0, 1)
+    return out
+
+
+def _mesh_args(mesh):
+    return (C.c_int(mesh.numRegions), _p(mesh.adjOffset, C.c_int32), _p(mesh.adjList, C.c_int32))
+
+
+def neighbor_dist(mesh, xyz):
+    out = np.empty(mesh.adjList.shape[0], np.float32)
+    lib().orc_neighbor_dist(*_mesh_args(mesh), _p(xyz, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def warp_terrain(mesh, elev, xyz, seed, strength, hotspot=None):
+    lib().orc_warp_terrain(*_mesh_args(mesh), _p(elev, C.c_float), _p(xyz, C.c_float), C.c_double(seed),
+                           C.c_double(strength), _opt(hotspot, C.c_float))
+
+
+def smooth_elevation(mesh, elev, is_ocean, iterations, strength):
+    lib().orc_smooth_elevation(*_mesh_args(mesh), _p(elev, C.c_float), _p(is_ocean, C.c_uint8),
+                               C.c_int(iterations), C.c_double(strength))
+
+
+def priority_flood_carve(mesh, elev, is_ocean, carve_strength):
+    n = mesh.numRegions
+    drain = np.empty(n, np.int32)
+    surf = np.empty(n, np.float32)
+    openo = np.empty(n, np.uint8)
+    lib().orc_priority_flood_carve(*_mesh_args(mesh), _p(elev, C.c_float), _p(is_ocean, C.c_uint8),
+                                   C.c_double(carve_strength), _p(drain, C.c_int32), _p(surf, C.c_float),
+                                   _p(openo, C.c_uint8))
+    return drain, surf, openo
+
+
+def erode_composite(mesh, elev, xyz, is_ocean, hIters, K, m, dt, tIters, talus, kThermal, gIters,
+                    glacialStrength, neighborDist, capture_iter=-1):
+    n = mesh.numRegions
+    dt_ = np.full(n, -2, np.int32)
+    fl = np.zeros(n, np.float32)
+    lo = np.full(n, -1, np.int32)
+    lib().orc_erode_composite(*_mesh_args(mesh), _p(elev, C.c_float), _p(xyz, C.c_float),
+                              _p(is_ocean, C.c_uint8), C.c_int(hIters), C.c_double(K), C.c_double(m),
+                              C.c_double(dt), C.c_int(tIters), C.c_double(talus), C.c_double(kThermal),
+                              C.c_int(gIters), C.c_double(glacialStrength), _p(neighborDist, C.c_float),
+                              C.c_int(capture_iter), _p(dt_, C.c_int32), _p(fl, C.c_float), _p(lo, C.c_int32))
+    return dt_, fl, lo
+
+
+def sharpen_ridges(mesh, elev, is_ocean, iterations, strength):
+    lib().orc_sharpen_ridges(*_mesh_args(mesh), _p(elev, C.c_float), _p(is_ocean, C.c_uint8),
+                             C.c_int(iterations), C.c_double(strength))
+
+
+def apply_soil_creep(mesh, elev, is_ocean, iterations, strength):
+    lib().orc_apply_soil_creep(*_mesh_args(mesh), _p(elev, C.c_float), _p(is_ocean, C.c_uint8),
+                               C.c_int(iterations), C.c_double(strength))
+
+
+def run_post_processing(mesh, xyz, elev, params, neighborDist, seed, hotspot=None, h_iters_override=-1):
+    n = mesh.numRegions
+    delta = np.empty(n, np.float32)
+    is_ocean = np.empty(n, np.uint8)
+    lib().orc_run_post_processing(
+        *_mesh_args(mesh), _p(xyz, C.c_float), _p(elev, C.c_float),
+        C.c_double(params["smoothing"]), C.c_double(params["glacialErosion"]),
+        C.c_double(params["hydraulicErosion"]), C.c_double(params["thermalErosion"]),
+        C.c_double(params["ridgeSharpening"]), C.c_double(params["terrainWarp"]),
+        C.c_int(h_iters_override), _p(neighborDist, C.c_float), C.c_double(seed),
+        _opt(hotspot, C.c_float), _p(delta, C.c_float), _p(is_ocean, C.c_uint8))
+    return delta, is_ocean
+
+
+def smooth_field(mesh, field, passes):
+    lib().orc_smooth_field(*_mesh_args(mesh), _p(field, C.c_float), C.c_int(passes))
+
+
+def percentile(arr, p):
+    arr = np.ascontiguousarray(arr, np.float32)
+    return lib().orc_percentile(_p(arr, C.c_float), C.c_int(arr.size), C.c_double(p))
