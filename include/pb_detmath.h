@@ -255,12 +255,33 @@ PB_HD void pb_sincos(double x, double* s, double* c) {
 PB_HD double pb_sin(double x) { double s, c; pb_sincos(x, &s, &c); return s; }
 PB_HD double pb_cos(double x) { double s, c; pb_sincos(x, &s, &c); return c; }
 
+/* exp(r) - 1 for |r| <= 0.35 without cancellation (same Horner polynomial as pb_exp_hl). */
+PB_HD double pb_expm1_small(double r) {
+    double p = 1.0 / 355687428096000.0;
+    p = p * r + 1.0 / 20922789888000.0;
+    p = p * r + 1.0 / 1307674368000.0;
+    p = p * r + 1.0 / 87178291200.0;
+    p = p * r + 1.0 / 6227020800.0;
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    return r + r * r * p;
+}
+
 PB_HD double pb_tanh(double x) {
     if (x != x) return x;
     double ax = x < 0 ? -x : x;
     double r;
     if (ax > 22.0) r = 1.0;
-    else if (ax < 1e-8) r = ax;
+    else if (ax < 0.17) { double t = pb_expm1_small(2.0 * ax); r = t / (t + 2.0); }
     else { double e = pb_exp(2.0 * ax); r = 1.0 - 2.0 / (e + 1.0); }
     return x < 0 ? -r : r;
 }

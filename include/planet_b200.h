@@ -1,0 +1,135 @@
+/*
+ * planet_b200.h — C ABI of the B200-native planet-heightmap engine.
+ *
+ * This is the drop-in boundary for the per-Voronoi-cell hot path of
+ * raguilar011095/planet_heightmap_generation.  The reference has no native layer: its hot path is
+ * a set of plain exported JavaScript functions over typed arrays, called from the Web-Worker
+ * command layer (js/planet-worker.js).  Each entry point below replaces one of those functions
+ * and cites it.  A Node N-API addon / ctypes stub binds them 1:1.
+ *
+ * Conventions
+ *  - Every function returns pb_status (0 = PB_OK).  On failure pb_last_error() returns a message
+ *    for the calling thread (the reference's handlers turn exceptions into
+ *    {type:'error', message}; js/planet-worker.js:336-338).
+ *  - A pb_context owns one CUDA device + stream.  Calls on one context are synchronous with respect
+ *    to the caller in host-pointer mode and are NOT re-entrant (the reference runs one worker,
+ *    one command at a time; js/planet-worker.js:944-954).
+ *  - Per-cell array arguments follow the context's pointer mode (like cuBLAS pointer mode):
+ *      PB_POINTER_HOST   (default) host arrays; the call copies in, computes on the GPU, copies out
+ *                        and returns when the result is in the caller's buffer.
+ *      PB_POINTER_DEVICE device arrays already resident in HBM; the call only enqueues work on the
+ *                        context's stream (results are ordered on that stream).
+ *    Mesh construction always takes host arrays.
+ *  - `r_elevation` is mutated in place, exactly like the reference functions do.
+ *  - `seed` is a double: the reference passes non-integer seeds (js/plates.js:9).
+ *  - Layouts are the reference's: adjOffset int32[N+1], adjList int32[E], r_xyz float32[3N] (AoS),
+ *    per-cell fields float32[N] / int32[N] / uint8[N], per-edge fields float32[E].
+ */
+#ifndef PLANET_B200_H
+#define PLANET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int pb_status;
+#define PB_OK 0
+#define PB_ERR_INVALID 1
+#define PB_ERR_CUDA 2
+#define PB_ERR_INTERNAL 3
+
+#define PB_POINTER_HOST 0
+#define PB_POINTER_DEVICE 1
+
+typedef struct pb_context pb_context;
+typedef struct pb_mesh pb_mesh;
+
+/* ---- context ------------------------------------------------------------------------------- */
+pb_status pb_context_create(int device, pb_context** out);
+void pb_context_destroy(pb_context* ctx);
+const char* pb_last_error(void);
+const char* pb_version(void);
+/* cuda_stream is a cudaStream_t (NULL = default stream). */
+pb_status pb_set_stream(pb_context* ctx, void* cuda_stream);
+pb_status pb_set_pointer_mode(pb_context* ctx, int mode);
+pb_status pb_synchronize(pb_context* ctx);
+/* kernels launched by this library on any context since process start (bench: gpu_launches) */
+int64_t pb_launch_count(void);
+
+/* ---- mesh ------------------------------------------------------------------------------------
+ * Replaces the `mesh` object the hot-path functions receive: {numRegions, adjOffset, adjList}
+ * (js/sphere-mesh.js:94-146) plus r_xyz (js/sphere-mesh.js:174-186).  neighborDist
+ * (computeNeighborDist, js/sphere-mesh.js:191-203) is computed on the device at creation and kept
+ * with the mesh; the reference passes it to erodeComposite as a separate argument. */
+pb_status pb_mesh_create(pb_context* ctx, int32_t numRegions, const int32_t* adjOffset,
+                         const int32_t* adjList, const float* r_xyz, pb_mesh** out);
+void pb_mesh_destroy(pb_mesh* mesh);
+int32_t pb_mesh_num_regions(const pb_mesh* mesh);
+int64_t pb_mesh_num_edges(const pb_mesh* mesh);
+/* computeNeighborDist(mesh, r_xyz) → Float32Array[E]            js/sphere-mesh.js:191-203 */
+pb_status pb_compute_neighbor_dist(pb_mesh* mesh, float* neighborDist_out);
+
+/* ---- terrain-post (js/terrain-post.js) -------------------------------------------------------- */
+/* warpTerrain(mesh, r_elevation, r_xyz, seed, strength, r_hotspot)      js/terrain-post.js:233-309
+ * r_hotspot may be NULL (handleReapply passes none, js/planet-worker.js:358). */
+pb_status pb_warp_terrain(pb_mesh* mesh, float* r_elevation, double seed, double strength,
+                          const float* r_hotspot);
+/* smoothElevation(mesh, r_elevation, r_isOcean, iterations, strength)  js/terrain-post.js:317-354 */
+pb_status pb_smooth_elevation(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                              int32_t iterations, double strength);
+/* priorityFloodCarve(mesh, r_elevation, r_isOcean, carveStrength)      js/terrain-post.js:59-215
+ * (module-private in the reference; exported here because erodeComposite calls it twice and the
+ * parity tests tap it).  Optional outputs (NULL to skip): drainTo int32[N], surface float32[N],
+ * isOpenOcean uint8[N] — the state after pass 1. */
+pb_status pb_priority_flood_carve(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                                  double carveStrength, int32_t* drainTo_out, float* surface_out,
+                                  uint8_t* isOpenOcean_out);
+/* erodeComposite(mesh, r_elevation, r_xyz, r_isOcean, hIters, K, m, dt, tIters, talusSlope,
+ *                kThermal, gIters, glacialStrength, neighborDist)       js/terrain-post.js:369-707 */
+pb_status pb_erode_composite(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                             int32_t hIters, double K, double m, double dt, int32_t tIters,
+                             double talusSlope, double kThermal, int32_t gIters,
+                             double glacialStrength);
+/* Same, plus taps on hydraulic iteration `captureIter` taken right before the implicit solve:
+ * drainTarget int32[N] (the drainage-receiver field), flow float32[N], landOrder int32[N] (the
+ * sorted landCells, -1 padded).  Any tap may be NULL. */
+pb_status pb_erode_composite_debug(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                                   int32_t hIters, double K, double m, double dt, int32_t tIters,
+                                   double talusSlope, double kThermal, int32_t gIters,
+                                   double glacialStrength, int32_t captureIter,
+                                   int32_t* drainTarget_out, float* flow_out, int32_t* landOrder_out);
+/* sharpenRidges(mesh, r_elevation, r_isOcean, iterations, strength)    js/terrain-post.js:713-751 */
+pb_status pb_sharpen_ridges(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                            int32_t iterations, double strength);
+/* applySoilCreep(mesh, r_elevation, r_isOcean, iterations, strength)   js/terrain-post.js:758-794 */
+pb_status pb_apply_soil_creep(pb_mesh* mesh, float* r_elevation, const uint8_t* r_isOcean,
+                              int32_t iterations, double strength);
+
+/* runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot)
+ *                                                                     js/planet-worker.js:40-102
+ * Slider values as the worker receives them.  hItersOverride >= 0 replaces round(20*hydraulic)
+ * while K stays 0.0006*hydraulic (BASELINE.json configs 2 and 5 ask for 50 / 200 iterations, more
+ * than the UI slider can request).  Outputs: erosionDelta float32[N] (dl_erosionDelta) and, when
+ * not NULL, the r_isOcean mask the pipeline derived after the warp (uint8[N]). */
+typedef struct pb_post_params {
+    double smoothing, glacialErosion, hydraulicErosion, thermalErosion, ridgeSharpening, terrainWarp;
+    int32_t hItersOverride;
+} pb_post_params;
+pb_status pb_run_post_processing(pb_mesh* mesh, float* r_elevation, const pb_post_params* params,
+                                 double seed, const float* r_hotspot, float* erosionDelta_out,
+                                 uint8_t* r_isOcean_out);
+
+/* per-stage device time of the last pb_run_post_processing (CUDA events), same stage order as the
+ * reference's postTiming array: warp, smoothing, erosion, ridge, creep.  ms_out: double[5]. */
+pb_status pb_last_post_timing(pb_mesh* mesh, double* ms_out);
+
+/* ---- climate-util (js/climate-util.js) --------------------------------------------------------- */
+/* smoothField(mesh, field, passes)                                    js/climate-util.js:5-25 */
+pb_status pb_smooth_field(pb_mesh* mesh, float* field, int32_t passes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANET_B200_H */

@@ -1,0 +1,237 @@
+// pb_platform.h — execution layer shared by every kernel of the engine.
+//
+// Product build:  nvcc -gencode arch=compute_100a,code=sm_100a  (PB_CUDA == 1).  Every per-cell
+// functor below becomes a __global__ grid-stride kernel; ordered (class S) functors become
+// ticketed sync-free dataflow kernels.
+//
+// PB_EMUL build (tests/emul only, g++): the same functors are run by a sequential loop so the
+// host orchestration and the per-cell logic can be checked against the oracle on a box without a
+// GPU.  It is test infrastructure — the python package never loads it (see _lib.py).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <algorithm>
+
+#if defined(__CUDACC__) && !defined(PB_EMUL)
+#define PB_CUDA 1
+#include <cuda_runtime.h>
+#define PB_DEV __device__ __forceinline__
+#define PB_GLOBAL __global__
+#else
+#define PB_CUDA 0
+#define PB_DEV inline
+typedef void* cudaStream_t;
+#endif
+
+#include "../../include/pb_detmath.h"
+
+namespace pb {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#if PB_CUDA
+#define PB_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            throw pb::Error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+    } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------------------------
+inline void* dev_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+#if PB_CUDA
+    void* p = nullptr;
+    PB_CUDA_CHECK(cudaMalloc(&p, bytes));
+    return p;
+#else
+    void* p = malloc(bytes);
+    if (!p) throw Error("malloc failed");
+    return p;
+#endif
+}
+inline void dev_free(void* p) {
+    if (!p) return;
+#if PB_CUDA
+    cudaFree(p);
+#else
+    free(p);
+#endif
+}
+inline void dev_memset(void* p, int v, size_t bytes, cudaStream_t s) {
+#if PB_CUDA
+    PB_CUDA_CHECK(cudaMemsetAsync(p, v, bytes, s));
+#else
+    memset(p, v, bytes);
+#endif
+}
+// kind: 0 h2d, 1 d2h, 2 d2d
+inline void dev_copy(void* dst, const void* src, size_t bytes, int kind, cudaStream_t s) {
+    if (bytes == 0) return;
+#if PB_CUDA
+    cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    PB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, k, s));
+#else
+    memmove(dst, src, bytes);
+#endif
+}
+inline void stream_sync(cudaStream_t s) {
+#if PB_CUDA
+    PB_CUDA_CHECK(cudaStreamSynchronize(s));
+#endif
+}
+
+// Typed device buffer that grows on demand and is reused between calls (no per-call cudaMalloc
+// once a context is warm).
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { dev_free(p); }
+    T* ensure(size_t n) {
+        if (n > cap) {
+            dev_free(p);
+            p = nullptr;
+            cap = 0;
+            p = (T*)dev_alloc(n * sizeof(T));
+            cap = n;
+        }
+        return p;
+    }
+    operator T*() const { return p; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device-side primitives
+// ---------------------------------------------------------------------------------------------
+#if PB_CUDA
+PB_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+PB_DEV unsigned long long atomic_max64(unsigned long long* p, unsigned long long v) { return atomicMax(p, v); }
+PB_DEV int atomic_min(int* p, int v) { return atomicMin(p, v); }
+PB_DEV int atomic_max(int* p, int v) { return atomicMax(p, v); }
+PB_DEV int atomic_cas(int* p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+PB_DEV void fence() { __threadfence(); }
+PB_DEV int ld_volatile(const int* p) { return *(const volatile int*)p; }
+// L2-coherent loads/stores for data exchanged between CTAs inside one ordered kernel
+PB_DEV float ld_cg(const float* p) { return __ldcg(p); }
+PB_DEV int ld_cg(const int* p) { return __ldcg(p); }
+PB_DEV void st_cg(float* p, float v) { __stcg(p, v); }
+PB_DEV void st_cg(int* p, int v) { __stcg(p, v); }
+#else
+PB_DEV int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+PB_DEV unsigned long long atomic_max64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
+PB_DEV int atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+PB_DEV int atomic_max(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+PB_DEV int atomic_cas(int* p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
+PB_DEV void fence() {}
+PB_DEV int ld_volatile(const int* p) { return *p; }
+PB_DEV float ld_cg(const float* p) { return *p; }
+PB_DEV int ld_cg(const int* p) { return *p; }
+PB_DEV void st_cg(float* p, float v) { *p = v; }
+PB_DEV void st_cg(int* p, int v) { *p = v; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+struct LaunchStats {
+    long long launches = 0;  // kernels launched through this layer since the last reset
+};
+inline LaunchStats& launch_stats() {
+    static LaunchStats s;
+    return s;
+}
+
+#if PB_CUDA
+template <class F>
+PB_GLOBAL void __launch_bounds__(256) k_for(F f, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f(i);
+}
+
+// Sync-free ordered dataflow: item i may only depend on items j < i.  CTAs take a ticket so the
+// logical CTA order equals the order in which CTAs became resident — every dependency of a
+// resident item is resident or finished, hence the polling loop cannot deadlock.  Lanes never
+// block on one another: a lane whose dependencies are not yet met simply retries.
+template <class F>
+PB_GLOBAL void __launch_bounds__(128) k_ordered(F f, int n, int* ticket) {
+    __shared__ int base;
+    if (threadIdx.x == 0) base = atomicAdd(ticket, 1) * blockDim.x;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    bool pending = i < n;
+    while (pending) {
+        if (f.try_run(i)) pending = false;
+    }
+}
+
+template <class F>
+PB_GLOBAL void k_single(F f) {
+    f();
+}
+#endif
+
+struct Exec {
+    cudaStream_t stream = 0;
+    int sm_count = 148;
+    int* ticket = nullptr;  // device int used by ordered launches
+
+    template <class F>
+    void for_each(int n, const F& f) const {
+        if (n <= 0) return;
+        launch_stats().launches++;
+#if PB_CUDA
+        const int block = 256;
+        long long want = ((long long)n + block - 1) / block;
+        int grid = (int)std::min<long long>(want, (long long)sm_count * 16);
+        k_for<F><<<grid, block, 0, stream>>>(f, n);
+        PB_CUDA_CHECK(cudaGetLastError());
+#else
+        for (int i = 0; i < n; i++) f(i);
+#endif
+    }
+
+    template <class F>
+    void ordered(int n, const F& f) const {
+        if (n <= 0) return;
+        launch_stats().launches++;
+#if PB_CUDA
+        const int block = 128;
+        PB_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(int), stream));
+        int grid = (n + block - 1) / block;
+        k_ordered<F><<<grid, block, 0, stream>>>(f, n, ticket);
+        PB_CUDA_CHECK(cudaGetLastError());
+#else
+        for (int i = 0; i < n; i++) {
+            if (!f.try_run(i)) throw Error("ordered dataflow: dependency of a later item (emulation)");
+        }
+#endif
+    }
+
+    // one logical thread (serial kernels: heap flood)
+    template <class F>
+    void single(const F& f) const {
+        launch_stats().launches++;
+#if PB_CUDA
+        k_single<F><<<1, 1, 0, stream>>>(f);
+        PB_CUDA_CHECK(cudaGetLastError());
+#else
+        f();
+#endif
+    }
+};
+
+}  // namespace pb

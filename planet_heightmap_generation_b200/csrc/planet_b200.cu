@@ -1,0 +1,219 @@
+// planet_b200.cu — extern "C" surface declared in include/planet_b200.h.
+// Compiled by nvcc for sm_100a into libplanet_b200.so (product), or by g++ with -DPB_EMUL into the
+// test-only host emulation used by the CPU test-suite (tests/emul/).
+#include "pb_engine.h"
+
+namespace {
+thread_local std::string g_err;
+
+template <class F>
+pb_status guard(F&& f) {
+    try {
+        f();
+        return PB_OK;
+    } catch (const pb::Error& e) {
+        g_err = e.what();
+        return PB_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        g_err = e.what();
+        return PB_ERR_INVALID;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return PB_ERR_INTERNAL;
+    }
+}
+void need(bool c, const char* what) {
+    if (!c) throw std::invalid_argument(what);
+}
+}  // namespace
+
+struct pb_context { pb::Context c; explicit pb_context(int d) : c(d) {} };
+struct pb_mesh {
+    pb::Mesh m;
+    pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
+};
+
+extern "C" {
+
+const char* pb_last_error(void) { return g_err.c_str(); }
+const char* pb_version(void) {
+#if PB_CUDA
+    return "planet_b200 0.1 (cuda sm_100a)";
+#else
+    return "planet_b200 0.1 (HOST EMULATION — test only)";
+#endif
+}
+int64_t pb_launch_count(void) { return pb::launch_stats().launches; }
+
+pb_status pb_context_create(int device, pb_context** out) {
+    return guard([&] {
+        need(out != nullptr, "out is NULL");
+#if PB_CUDA
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw pb::Error("no CUDA device available: this library has no CPU path");
+        need(device >= 0 && device < n, "device index out of range");
+#endif
+        *out = new pb_context(device);
+    });
+}
+void pb_context_destroy(pb_context* ctx) { delete ctx; }
+pb_status pb_set_stream(pb_context* ctx, void* s) {
+    return guard([&] { need(ctx, "ctx is NULL"); ctx->c.ex.stream = (cudaStream_t)s; });
+}
+pb_status pb_set_pointer_mode(pb_context* ctx, int mode) {
+    return guard([&] {
+        need(ctx, "ctx is NULL");
+        need(mode == PB_POINTER_HOST || mode == PB_POINTER_DEVICE, "unknown pointer mode");
+        ctx->c.pointerMode = mode;
+    });
+}
+pb_status pb_synchronize(pb_context* ctx) {
+    return guard([&] { need(ctx, "ctx is NULL"); ctx->c.bind(); pb::stream_sync(ctx->c.ex.stream); });
+}
+
+pb_status pb_mesh_create(pb_context* ctx, int32_t n, const int32_t* off, const int32_t* adj, const float* xyz, pb_mesh** out) {
+    return guard([&] {
+        need(ctx && off && adj && xyz && out, "NULL argument");
+        ctx->c.bind();
+        *out = new pb_mesh(&ctx->c, n, off, adj, xyz);
+    });
+}
+void pb_mesh_destroy(pb_mesh* mesh) { delete mesh; }
+int32_t pb_mesh_num_regions(const pb_mesh* mesh) { return mesh ? mesh->m.N : 0; }
+int64_t pb_mesh_num_edges(const pb_mesh* mesh) { return mesh ? mesh->m.E : 0; }
+
+pb_status pb_compute_neighbor_dist(pb_mesh* mesh, float* out) {
+    return guard([&] {
+        need(mesh && out, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        if (m.hostMode()) pb::dev_copy(out, m.ndist.p, sizeof(float) * (size_t)m.E, 1, m.ex().stream);
+        else pb::dev_copy(out, m.ndist.p, sizeof(float) * (size_t)m.E, 2, m.ex().stream);
+        m.finish();
+    });
+}
+
+pb_status pb_smooth_field(pb_mesh* mesh, float* field, int32_t passes) {
+    return guard([&] {
+        need(mesh && field, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        float* d = m.arg_in(field, m.N, m.sField);
+        m.smooth_field(d, passes);
+        m.arg_back(field, d, m.N);
+        m.finish();
+    });
+}
+
+pb_status pb_warp_terrain(pb_mesh* mesh, float* elev, double seed, double strength, const float* hotspot) {
+    return guard([&] {
+        need(mesh && elev, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        float* d = m.arg_in(elev, m.N, m.sElev);
+        const float* h = m.arg_in(hotspot, m.N, m.sHot);
+        m.warp_terrain(d, seed, strength, h);
+        m.arg_back(elev, d, m.N);
+        m.finish();
+    });
+}
+
+#define PB_ELEV_OCEAN_PROLOGUE                                   \
+    need(mesh && elev && isOcean, "NULL argument");              \
+    pb::Mesh& m = mesh->m; m.ctx->bind();                        \
+    float* d = m.arg_in(elev, m.N, m.sElev);                     \
+    const uint8_t* o = m.arg_in(isOcean, m.N, m.sOcean);
+
+pb_status pb_smooth_elevation(pb_mesh* mesh, float* elev, const uint8_t* isOcean, int32_t iterations, double strength) {
+    return guard([&] {
+        PB_ELEV_OCEAN_PROLOGUE
+        m.smooth_elevation(d, o, iterations, strength);
+        m.arg_back(elev, d, m.N);
+        m.finish();
+    });
+}
+pb_status pb_sharpen_ridges(pb_mesh* mesh, float* elev, const uint8_t* isOcean, int32_t iterations, double strength) {
+    return guard([&] {
+        PB_ELEV_OCEAN_PROLOGUE
+        m.sharpen_ridges(d, o, iterations, strength);
+        m.arg_back(elev, d, m.N);
+        m.finish();
+    });
+}
+pb_status pb_apply_soil_creep(pb_mesh* mesh, float* elev, const uint8_t* isOcean, int32_t iterations, double strength) {
+    return guard([&] {
+        PB_ELEV_OCEAN_PROLOGUE
+        m.apply_soil_creep(d, o, iterations, strength);
+        m.arg_back(elev, d, m.N);
+        m.finish();
+    });
+}
+
+pb_status pb_priority_flood_carve(pb_mesh* mesh, float* elev, const uint8_t* isOcean, double carveStrength,
+                                  int32_t* drainTo, float* surface, uint8_t* openOcean) {
+    return guard([&] {
+        PB_ELEV_OCEAN_PROLOGUE
+        pb::FloodTaps t;
+        t.drainTo = m.arg_out(drainTo, m.N, m.sI0);
+        t.surface = m.arg_out(surface, m.N, m.sField);
+        t.openOcean = m.arg_out(openOcean, m.N, m.sU8);
+        m.priority_flood_carve(d, o, carveStrength, &t);
+        m.arg_back(elev, d, m.N);
+        m.arg_back(drainTo, t.drainTo, m.N);
+        m.arg_back(surface, t.surface, m.N);
+        m.arg_back(openOcean, t.openOcean, m.N);
+        m.finish();
+    });
+}
+
+pb_status pb_erode_composite_debug(pb_mesh* mesh, float* elev, const uint8_t* isOcean, int32_t hIters, double K,
+                                   double mm, double dt, int32_t tIters, double talus, double kThermal, int32_t gIters,
+                                   double glacialStrength, int32_t captureIter, int32_t* drainTarget, float* flow,
+                                   int32_t* landOrder) {
+    return guard([&] {
+        PB_ELEV_OCEAN_PROLOGUE
+        pb::ErodeTaps t;
+        t.captureIter = captureIter;
+        t.drainTarget = m.arg_out(drainTarget, m.N, m.sI0);
+        t.flow = m.arg_out(flow, m.N, m.sField);
+        t.landOrder = m.arg_out(landOrder, m.N, m.sI1);
+        m.erode_composite(d, o, hIters, K, mm, dt, tIters, talus, kThermal, gIters, glacialStrength, &t);
+        m.arg_back(elev, d, m.N);
+        m.arg_back(drainTarget, t.drainTarget, m.N);
+        m.arg_back(flow, t.flow, m.N);
+        m.arg_back(landOrder, t.landOrder, m.N);
+        m.finish();
+    });
+}
+pb_status pb_erode_composite(pb_mesh* mesh, float* elev, const uint8_t* isOcean, int32_t hIters, double K, double mm,
+                             double dt, int32_t tIters, double talus, double kThermal, int32_t gIters,
+                             double glacialStrength) {
+    return pb_erode_composite_debug(mesh, elev, isOcean, hIters, K, mm, dt, tIters, talus, kThermal, gIters,
+                                    glacialStrength, -1, nullptr, nullptr, nullptr);
+}
+
+pb_status pb_run_post_processing(pb_mesh* mesh, float* elev, const pb_post_params* p, double seed, const float* hotspot,
+                                 float* erosionDelta, uint8_t* isOceanOut) {
+    return guard([&] {
+        need(mesh && elev && p, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        float* d = m.arg_in(elev, m.N, m.sElev);
+        const float* h = m.arg_in(hotspot, m.N, m.sHot);
+        float* dd = m.arg_out(erosionDelta, m.N, m.sDelta);
+        uint8_t* oo = m.arg_out(isOceanOut, m.N, m.sOcean);
+        m.run_post_processing(d, *p, seed, h, dd, oo);
+        m.arg_back(elev, d, m.N);
+        m.arg_back(erosionDelta, dd, m.N);
+        m.arg_back(isOceanOut, oo, m.N);
+        m.finish();
+    });
+}
+
+pb_status pb_last_post_timing(pb_mesh* mesh, double* ms) {
+    return guard([&] {
+        need(mesh && ms, "NULL argument");
+        mesh->m.ctx->bind();
+        mesh->m.timer.resolve();
+        for (int i = 0; i < 5; i++) ms[i] = mesh->m.timer.ms[i];
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+"""Device-resident mesh + context: the object that stands in for the reference's `mesh` argument.
+
+Every hot-path function of the reference takes `mesh` ({numRegions, adjOffset, adjList},
+js/sphere-mesh.js:94-146) and `r_xyz`.  `DeviceMesh` uploads both once and keeps them (and
+neighborDist) in HBM, like the worker's retained state `W` (js/planet-worker.js:277-292).
+
+Array arguments may be numpy arrays (host buffers: copied in and out by the C ABI, the call blocks)
+or torch CUDA tensors (already resident: work is only enqueued on torch's current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Library, PlanetB200Error, PostParams, default_library
+
+_NP = {"f32": np.float32, "i32": np.int32, "u8": np.uint8}
+
+
+def _is_torch_cuda(a) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+class DeviceMesh:
+    def __init__(self, mesh, r_xyz, device: int = 0, lib: Library | None = None):
+        self.lib = lib or default_library()
+        self.numRegions = int(mesh.numRegions)
+        self.adjOffset = np.ascontiguousarray(mesh.adjOffset, np.int32)
+        self.adjList = np.ascontiguousarray(mesh.adjList, np.int32)
+        self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
+        if self.adjOffset.shape[0] != self.numRegions + 1:
+            raise ValueError("adjOffset must have numRegions + 1 entries")
+        if self.r_xyz.shape[0] != 3 * self.numRegions:
+            raise ValueError("r_xyz must have 3 * numRegions entries")
+        self.numEdges = int(self.adjList.shape[0])
+        self.device = device
+        self._ctx = C.c_void_p()
+        self._mesh = C.c_void_p()
+        d = self.lib.dll
+        self.lib.check(d.pb_context_create(device, C.byref(self._ctx)))
+        self.lib.check(d.pb_mesh_create(self._ctx, self.numRegions, self.adjOffset.ctypes.data,
+                                        self.adjList.ctypes.data, self.r_xyz.ctypes.data, C.byref(self._mesh)))
+        self._mode = _lib.POINTER_HOST
+
+    def close(self):
+        if getattr(self, "_mesh", None):
+            self.lib.dll.pb_mesh_destroy(self._mesh)
+            self._mesh = None
+        if getattr(self, "_ctx", None):
+            self.lib.dll.pb_context_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- argument marshalling ---------------------------------------------------------------------
+    def _begin(self, *arrays):
+        """Pick the pointer mode from the argument types (all host or all device)."""
+        present = [a for a in arrays if a is not None]
+        dev = [_is_torch_cuda(a) for a in present]
+        if any(dev) and not all(dev):
+            raise TypeError("mix of host (numpy) and device (torch.cuda) arrays in one call")
+        mode = _lib.POINTER_DEVICE if (dev and dev[0]) else _lib.POINTER_HOST
+        if mode != self._mode:
+            self.lib.check(self.lib.dll.pb_set_pointer_mode(self._ctx, mode))
+            self._mode = mode
+        if mode == _lib.POINTER_DEVICE:
+            import torch
+            self.lib.check(self.lib.dll.pb_set_stream(self._ctx, torch.cuda.current_stream().cuda_stream))
+        return mode
+
+    def _ptr(self, a, kind: str, n: int, name: str, optional: bool = False):
+        if a is None:
+            if optional:
+                return None
+            raise ValueError(f"{name} is required")
+        if _is_torch_cuda(a):
+            import torch
+            want = {"f32": torch.float32, "i32": torch.int32, "u8": torch.uint8}[kind]
+            if a.dtype != want or not a.is_contiguous() or a.numel() != n:
+                raise ValueError(f"{name}: need a contiguous {want} CUDA tensor with {n} elements")
+            return a.data_ptr()
+        if not isinstance(a, np.ndarray) or a.dtype != _NP[kind] or not a.flags.c_contiguous or a.size != n:
+            raise ValueError(f"{name}: need a C-contiguous numpy {_NP[kind].__name__} array with {n} elements")
+        return a.ctypes.data
+
+    def _new(self, like, kind: str, n: int):
+        if _is_torch_cuda(like):
+            import torch
+            dt = {"f32": torch.float32, "i32": torch.int32, "u8": torch.uint8}[kind]
+            return torch.empty(n, dtype=dt, device=like.device)
+        return np.empty(n, _NP[kind])
+
+    def synchronize(self):
+        self.lib.check(self.lib.dll.pb_synchronize(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.dll.pb_launch_count())
+
+    # ---- mesh primitives ------------------------------------------------------------------------------
+    def computeNeighborDist(self, out=None):
+        """js/sphere-mesh.js:191-203"""
+        if out is None:
+            out = np.empty(self.numEdges, np.float32)
+        self._begin(out)
+        self.lib.check(self.lib.dll.pb_compute_neighbor_dist(self._mesh, self._ptr(out, "f32", self.numEdges, "out")))
+        return out

@@ -1,0 +1,95 @@
+"""Host-side generators for synthetic seeded planets (inputs of the hot path, not part of it).
+
+`fibonacci_sphere` follows js/sphere-mesh.js:9-37 (generateFibonacciSphere with makeRng jitter) in
+vectorised numpy; `build_sphere` adds the pole vertex and triangulates (mesh.py).  numpy's
+sin/cos/asin may differ from V8's in the last ulp of a double, which can flip an f32 store for a
+handful of points — irrelevant here because the same r_xyz array is handed to every implementation
+being compared.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mesh import build_sphere_from_points
+
+_M = 2147483647
+
+
+def park_miller(seed: float, n: int) -> np.ndarray:
+    """First n outputs of makeRng(seed) (js/rng.js:3-6), vectorised by jump-ahead."""
+    s0 = int(abs(np.floor(seed * 9301 + 49297)) % 2147483646) + 1
+    out = np.empty(n, np.float64)
+    B = 1 << 16
+    mult = np.empty(B, np.uint64)
+    a = 1
+    for k in range(B):
+        a = (a * 16807) % _M
+        mult[k] = a
+    s = s0
+    for start in range(0, n, B):
+        m = min(B, n - start)
+        states = (np.uint64(s) * mult[:m]) % np.uint64(_M)
+        out[start:start + m] = (states.astype(np.float64) - 1.0) / 2147483646.0
+        s = int(states[m - 1])
+    return out
+
+
+def fibonacci_sphere(N: int, jitter: float, seed: float) -> np.ndarray:
+    """r_xyz float32[3N] (js/sphere-mesh.js:9-37)."""
+    k = np.arange(N, dtype=np.float64)
+    s = 3.6 / np.sqrt(N)
+    dlong = np.pi * (3 - np.sqrt(5.0))
+    dz = 2.0 / N
+    # z is accumulated by repeated subtraction in the reference; reproduce that rounding
+    z = (1 - dz / 2) - np.concatenate(([0.0], np.cumsum(np.full(N - 1, dz))))
+    lng = np.concatenate(([0.0], np.cumsum(np.full(N - 1, dlong))))
+    r = np.sqrt(1 - z * z)
+    lat = np.arcsin(z) * 180 / np.pi
+    lon = lng * 180 / np.pi
+    if jitter > 0:
+        u = park_miller(seed, 4 * N).reshape(N, 4)
+        jlat = u[:, 0] - u[:, 1]
+        jlon = u[:, 2] - u[:, 3]
+        nextz = np.maximum(-1, z - dz * 2 * np.pi * r / s)
+        lat = lat + jitter * jlat * (lat - np.arcsin(nextz) * 180 / np.pi)
+        lon = lon + jitter * jlon * (s / r * 180 / np.pi)
+    latr = lat * np.pi / 180
+    lonr = lon * np.pi / 180
+    out = np.empty((N, 3), np.float32)
+    out[:, 0] = np.cos(latr) * np.cos(lonr)
+    out[:, 1] = np.cos(latr) * np.sin(lonr)
+    out[:, 2] = np.sin(latr)
+    return out.reshape(-1)
+
+
+def build_sphere(N: int, jitter: float, seed: float):
+    """buildSphere (js/sphere-mesh.js:174-186): N Fibonacci points + the pole vertex (0,0,1) as id N."""
+    xyz = np.empty(3 * (N + 1), np.float32)
+    xyz[:3 * N] = fibonacci_sphere(N, jitter, seed)
+    xyz[3 * N:] = (0, 0, 1)
+    return build_sphere_from_points(xyz)
+
+
+def synthetic_elevation(r_xyz: np.ndarray, seed: int, land_fraction: float = 0.3) -> np.ndarray:
+    """Seeded stand-in for assignElevation's output (`prePostElev`): a multi-octave random plane-wave
+    field on the sphere, shifted so that `land_fraction` of the cells are above sea level, with
+    continental relief of the reference's order of magnitude (land up to ≈1, ocean down to ≈-1)."""
+    p = np.asarray(r_xyz, np.float32).reshape(-1, 3).astype(np.float64)
+    rng = np.random.default_rng(seed)
+    h = np.zeros(p.shape[0])
+    amp_sum = 0.0
+    for octave in range(7):
+        f = 1.6 * 2.0 ** octave
+        a = 0.62 ** octave
+        for _ in range(4):
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            h += a * np.sin(f * (p @ d) + rng.uniform(0, 2 * np.pi))
+        amp_sum += 2 * a
+    h /= amp_sum
+    sea = np.quantile(h, 1 - land_fraction)
+    h = h - sea
+    h = np.where(h > 0, h / max(h.max(), 1e-9), h / max(-h.min(), 1e-9))
+    land = h > 0
+    h[land] = h[land] ** 0.8 * 0.9
+    return h.astype(np.float32)
