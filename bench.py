@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — Voronoi cells/s of the terrain-post hot path (BASELINE.json configs[1]).
+
+A "step" is one `reapply`-style pass (js/planet-worker.js:341-358): clone the pre-erosion elevation,
+then runPostProcessing (warp → smooth → erodeComposite with 50 stream-power iterations, 5 glacial,
+1 thermal, two priority floods → ridge sharpening → soil creep → erosionDelta) over a 1 000 001-cell
+Fibonacci-sphere Voronoi mesh, seed 42, sliders at the reference's UI defaults.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells C]
+
+own arm       value  = cells/s with the planet resident in HBM (device-pointer mode of the C ABI),
+                       CUDA-event timed, max over ranks; N>1 = N independent planets (replicas, weak).
+              e2e    = the same pass through the host-pointer C ABI (pinned host buffers in, results
+                       back in host memory), wall clock.
+              roofline / cpu_baseline as the task contract asks.
+reference arm the CPU oracle (oracle/, single thread like the reference's single Web Worker) on the
+              same workload.  The reference itself is JavaScript and no JS runtime exists in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SLIDERS = dict(smoothing=0.10, glacialErosion=0.50, hydraulicErosion=0.50, thermalErosion=0.10,
+               ridgeSharpening=0.50, terrainWarp=0.75)
+SEED = 42
+METRIC = "voronoi_cells_per_sec_terrain_post"
+UNIT = "cells/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic planet (cached on local disk: both arms and every rank use the same mesh)
+# ---------------------------------------------------------------------------------------------------
+def get_planet(cells: int, seed: int = SEED):
+    from planet_heightmap_generation_b200.mesh import SphereMesh, build_sphere_from_points
+    from planet_heightmap_generation_b200.sphere import fibonacci_sphere
+    cache_dir = os.path.join(tempfile.gettempdir(), "planet_b200_cache")
+    path = os.path.join(cache_dir, f"mesh_{cells}_{seed}.npz")
+    if os.path.exists(path):
+        try:
+            z = np.load(path)
+            return SphereMesh.from_csr(z["adjOffset"], z["adjList"]), z["r_xyz"]
+        except Exception:
+            pass
+    t = time.time()
+    xyz = np.empty(3 * (cells + 1), np.float32)
+    xyz[:3 * cells] = fibonacci_sphere(cells, 0.75, seed)
+    xyz[3 * cells:] = (0, 0, 1)
+    mesh, xyz = build_sphere_from_points(xyz)
+    log(f"[bench] built {cells}-cell mesh in {time.time() - t:.1f}s")
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        fd, tmp = tempfile.mkstemp(dir=cache_dir, suffix=".npz")
+        os.close(fd)
+        np.savez(tmp, adjOffset=mesh.adjOffset, adjList=mesh.adjList, r_xyz=xyz)
+        os.replace(tmp, path)
+    except Exception as e:   # cache is best effort
+        log(f"[bench] mesh cache not written: {e}")
+    return mesh, xyz
+
+
+def workload_name(cells, hiters):
+    return (f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), runPostProcessing with default sliders, "
+            f"hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, ridge 3, creep 3")
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=fd,
+                                         stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / baseline; never the product path)
+# ---------------------------------------------------------------------------------------------------
+def oracle_step_seconds(mesh, xyz, elev0, hiters, steps, warmup):
+    from oracle import binding as oracle
+    oracle.build()
+    nd = oracle.neighbor_dist(mesh, xyz)
+    times = []
+    for i in range(warmup + steps):
+        e = elev0.copy()
+        t = time.perf_counter()
+        oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, None, hiters)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation
+    mesh, xyz = get_planet(args.cells)
+    elev0 = synthetic_elevation(xyz, SEED, 0.3)
+    n = mesh.numRegions
+    times = oracle_step_seconds(mesh, xyz, elev0, args.hiters, args.steps, args.warmup)
+    total = float(np.sum(times))
+    v = n * len(times) / total
+    sample = f"full workload, {len(times)} timed passes of {n} cells after {args.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.cells, args.hiters),
+                   "note": "reference is browser JavaScript (one Web Worker, single thread); no JS runtime in this image, "
+                           "so this arm times oracle/ — the C++ -O2 restatement of the same functions — on one host core"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "cpu": cpu_model(), "host_cores": os.cpu_count()},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithmic bytes per launch of the kernels that can dominate (DESIGN.md §5 gives the derivation)
+# ---------------------------------------------------------------------------------------------------
+def algorithmic_bytes(name: str, N: int, E: int, land: int):
+    table = {
+        # order 4 + target 4 + cellDist 4 + flow 4 + elev r/w 8 + isOcean 1 per land cell
+        "pb::SolveK": 25 * land,
+        # order 4 + pos 4 + target 4 + contrib r/w 8 per land cell
+        "pb::AccumulateK": 20 * land,
+        # CSR 4N+4E + elev 4 + isOcean 1 + ndist 4E(land rows) + drainTarget 4 + cellDist 4
+        "pb::ReceiversK": 4 * N + 4 * E + 5 * N + int(4 * E * land / max(N, 1)) + 8 * land,
+        # key 4 + surface 4 + drainTo 4 + visited 1 + elev 4 + CSR row (4 + 4·6) + heap r/w 8 per flooded land cell
+        "pb::FloodSerialK": 53 * land,
+        "pb::SmoothFieldK": 4 * N + 4 * E + 8 * N,
+        "cub::DeviceRadixSort::SortPairs": 4 * 16 * land,
+    }
+    return table.get(name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation
+    from planet_heightmap_generation_b200.terrain_post import runPostProcessing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    mesh, xyz = get_planet(args.cells)
+    N, E = mesh.numRegions, int(mesh.adjList.shape[0])
+    # replicas: every rank erodes its own planet (same mesh, different terrain seed)
+    elev0_h = synthetic_elevation(xyz, SEED + rank, 0.3)
+    land = int((elev0_h > 0).sum())
+    dm = DeviceMesh(mesh, xyz, device=local)
+
+    elev0 = torch.from_numpy(elev0_h).to(dev)
+    elev = torch.empty_like(elev0)
+    delta = torch.empty_like(elev0)
+    ocean = torch.empty(N, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        flush.zero_()
+        elev.copy_(elev0)    # handleReapply clones W.prePostElev before post-processing (planet-worker.js:353)
+        runPostProcessing(dm, None, elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
+                          out_erosionDelta=delta, out_isOcean=ocean, timing=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    dominant = args.dominant
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = dm.launch_count()
+    dm.profile_start(dominant)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = dm.profile_stop()
+    launches = dm.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = N * world * args.steps / (ms_total / 1000.0)
+
+    # ---- end to end through the host-pointer C ABI ------------------------------------------------
+    h_elev0 = torch.from_numpy(elev0_h).pin_memory()
+    h_elev = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_delta = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_ocean = torch.empty(N, dtype=torch.uint8).pin_memory()
+    np_elev, np_delta, np_ocean = h_elev.numpy(), h_delta.numpy(), h_ocean.numpy()
+
+    def step_host():
+        flush.zero_()
+        h_elev.copy_(h_elev0)
+        runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
+                          out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = N * world * args.steps / e2e_s
+    same = bool((h_elev == elev.cpu()).all().item())   # host-pointer and device-pointer passes agree bit for bit
+
+    # ---- roofline of the dominant kernel (events recorded inside the timed region) ---------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roofline = None
+    dom = [p for p in prof if p["name"] == dominant or dominant in p["name"]]
+    if dom:
+        d = max(dom, key=lambda p: p["ms"])
+        ab = algorithmic_bytes(d["name"], N, E, land)
+        if ab:
+            avg_ms = d["ms"] / d["launches"]
+            achieved = ab / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": d["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": ab,
+                        "avg_launch_ms": avg_ms, "launches_timed": d["launches"],
+                        "share_of_step": d["ms"] / ms_total, "peak_source": peak_src}
+
+    # ---- one more fully profiled step: per-kernel breakdown (not part of any reported number) ---------
+    breakdown = None
+    if rank == 0 and not args.no_breakdown:
+        dm.profile_start(None)
+        step_device()
+        rows = sorted(dm.profile_stop(), key=lambda p: -p["ms"])
+        tot = sum(p["ms"] for p in rows)
+        breakdown = [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 3)} for p in rows[:12]]
+        log(f"[bench] per-kernel device time of one step (events around every launch, sum {tot:.1f} ms):")
+        for p in rows[:25]:
+            log(f"   {p['ms']:10.3f} ms  {p['launches']:6d}x  {p['name']}")
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        times = oracle_step_seconds(mesh, xyz, elev0_h, args.hiters, 1, 0)
+        cpu_baseline = {"value": N / times[0], "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread",
+                        "cpu": cpu_model(), "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.cells, args.hiters), "cells_per_gpu": N,
+                       "multi_gpu": "replicas (one planet per GPU, no data-path collective)" if world > 1 else "single",
+                       "l2": "256 MiB buffer written between steps (inside the timed region)",
+                       "land_cells": land},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * world,
+                    "d2h_bytes_per_step": 9 * N * world, "ms_per_step": 1000 * e2e_s / args.steps,
+                    "matches_device_path": same},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "kernel_breakdown": breakdown, "library": dm.lib.version,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=1_000_000)
+    ap.add_argument("--hiters", type=int, default=50)
+    ap.add_argument("--dominant", default="pb::SolveK", help="kernel whose launches are event-timed for the roofline")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-breakdown", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

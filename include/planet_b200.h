@@ -58,6 +58,13 @@ pb_status pb_synchronize(pb_context* ctx);
 /* kernels launched by this library on any context since process start (bench: gpu_launches) */
 int64_t pb_launch_count(void);
 
+/* Per-kernel device timing (the reference's counterpart is its performance.now() stage timers,
+ * js/planet-worker.js:42-101).  Between start and stop every launch of this library whose kernel
+ * name contains `filter` (NULL = all) is bracketed by CUDA events on the context's stream; stop
+ * synchronises and writes a JSON array [{"name":..,"launches":..,"ms":..}] into out[cap]. */
+pb_status pb_profile_start(pb_context* ctx, const char* filter);
+pb_status pb_profile_stop(pb_context* ctx, char* out, int64_t cap);
+
 /* ---- mesh ------------------------------------------------------------------------------------
  * Replaces the `mesh` object the hot-path functions receive: {numRegions, adjOffset, adjList}
  * (js/sphere-mesh.js:94-146) plus r_xyz (js/sphere-mesh.js:174-186).  neighborDist

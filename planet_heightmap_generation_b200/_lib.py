@@ -36,6 +36,8 @@ SYMBOLS = {
     "pb_set_pointer_mode": (C.c_int, [_vp, C.c_int]),
     "pb_synchronize": (C.c_int, [_vp]),
     "pb_launch_count": (_i64, []),
+    "pb_profile_start": (C.c_int, [_vp, C.c_char_p]),
+    "pb_profile_stop": (C.c_int, [_vp, C.c_char_p, _i64]),
     "pb_mesh_create": (C.c_int, [_vp, _i32, _vp, _vp, _vp, C.POINTER(_vp)]),
     "pb_mesh_destroy": (None, [_vp]),
     "pb_mesh_num_regions": (_i32, [_vp]),

@@ -20,6 +20,7 @@ struct Context {
     int pointerMode = PB_POINTER_HOST;
     Exec ex;
     DevBuf<int> ticket;
+    Profiler profiler;
     explicit Context(int dev) : device(dev) {
 #if PB_CUDA
         PB_CUDA_CHECK(cudaSetDevice(dev));
@@ -28,6 +29,7 @@ struct Context {
         ex.sm_count = prop.multiProcessorCount;
 #endif
         ex.ticket = ticket.ensure(4);
+        ex.prof = &profiler;
     }
     void bind() const {
 #if PB_CUDA

@@ -17,6 +17,8 @@
 #include <vector>
 #include <stdexcept>
 #include <algorithm>
+#include <typeinfo>
+#include <map>
 
 #if defined(__CUDACC__) && !defined(PB_EMUL)
 #define PB_CUDA 1
@@ -156,6 +158,72 @@ inline LaunchStats& launch_stats() {
     return s;
 }
 
+// Optional per-kernel device timing (bench / DESIGN evidence): when enabled, every launch whose
+// name contains `filter` is bracketed by two CUDA events on the launching stream.
+struct Profiler {
+    bool on = false;
+    std::string filter;
+#if PB_CUDA
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        PB_CUDA_CHECK(cudaEventCreate(&e));
+        return e;
+    }
+    ~Profiler() {
+        for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+#endif
+    bool wants(const char* name) const { return on && (filter.empty() || strstr(name, filter.c_str()) != nullptr); }
+    void start(const char* f) {
+        collect(nullptr);
+        filter = f ? f : "";
+        on = true;
+    }
+    // name -> (launches, total ms); empties the record list
+    void collect(std::map<std::string, std::pair<long long, double>>* out) {
+#if PB_CUDA
+        for (auto& r : recs) {
+            if (out) {
+                PB_CUDA_CHECK(cudaEventSynchronize(r.b));
+                float ms = 0;
+                PB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+                auto& e = (*out)[r.name];
+                e.first++;
+                e.second += ms;
+            }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+#endif
+    }
+};
+struct ProfScope {
+#if PB_CUDA
+    Profiler* p = nullptr;
+    cudaStream_t s;
+    cudaEvent_t a, b;
+    const char* name;
+    ProfScope(Profiler* prof, const char* nm, cudaStream_t st) : s(st), name(nm) {
+        if (prof && prof->wants(nm)) {
+            p = prof;
+            a = p->get(); b = p->get();
+            cudaEventRecord(a, s);
+        }
+    }
+    ~ProfScope() {
+        if (p) { cudaEventRecord(b, s); p->recs.push_back({name, a, b}); }
+    }
+#else
+    ProfScope(Profiler*, const char*, cudaStream_t) {}
+#endif
+};
+
 #if PB_CUDA
 template <class F>
 PB_GLOBAL void __launch_bounds__(256) k_for(F f, int n) {
@@ -188,11 +256,13 @@ struct Exec {
     cudaStream_t stream = 0;
     int sm_count = 148;
     int* ticket = nullptr;  // device int used by ordered launches
+    Profiler* prof = nullptr;
 
     template <class F>
     void for_each(int n, const F& f) const {
         if (n <= 0) return;
         launch_stats().launches++;
+        ProfScope ps(prof, typeid(F).name(), stream);
 #if PB_CUDA
         const int block = 256;
         long long want = ((long long)n + block - 1) / block;
@@ -208,6 +278,7 @@ struct Exec {
     void ordered(int n, const F& f) const {
         if (n <= 0) return;
         launch_stats().launches++;
+        ProfScope ps(prof, typeid(F).name(), stream);
 #if PB_CUDA
         const int block = 128;
         PB_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(int), stream));
@@ -225,6 +296,7 @@ struct Exec {
     template <class F>
     void single(const F& f) const {
         launch_stats().launches++;
+        ProfScope ps(prof, typeid(F).name(), stream);
 #if PB_CUDA
         k_single<F><<<1, 1, 0, stream>>>(f);
         PB_CUDA_CHECK(cudaGetLastError());

@@ -31,9 +31,14 @@ struct Prims {
     // out[0..count) = ascending indices i in [0,n) with flag[i] != 0; *dCount = count (device int)
     void compact_flagged(const Exec& ex, const uint8_t* flag, int n, int* out, int* dCount) {
         if (n <= 0) { dev_memset(dCount, 0, sizeof(int), ex.stream); return; }
-        launch_stats().launches++;
+        const int* idx = nullptr;
 #if PB_CUDA
-        const int* idx = ensure_iota(ex, n);
+        idx = ensure_iota(ex, n);
+#endif
+        (void)idx;
+        launch_stats().launches++;
+        ProfScope ps(ex.prof, "cub::DeviceSelect::Flagged", ex.stream);
+#if PB_CUDA
         size_t bytes = 0;
         PB_CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, bytes, idx, flag, out, dCount, n, ex.stream));
         temp.ensure(bytes);
@@ -49,6 +54,7 @@ struct Prims {
     void sort_pairs(const Exec& ex, uint32_t* keys, int* vals, int n, bool descending, int endBit = 32) {
         if (n <= 1) return;
         launch_stats().launches++;
+        ProfScope ps(ex.prof, "cub::DeviceRadixSort::SortPairs", ex.stream);
 #if PB_CUDA
         kAlt.ensure(n);
         vAlt.ensure(n);

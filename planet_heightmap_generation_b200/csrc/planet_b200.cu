@@ -2,6 +2,7 @@
 // Compiled by nvcc for sm_100a into libplanet_b200.so (product), or by g++ with -DPB_EMUL into the
 // test-only host emulation used by the CPU test-suite (tests/emul/).
 #include "pb_engine.h"
+#include <cxxabi.h>
 
 namespace {
 thread_local std::string g_err;
@@ -70,6 +71,36 @@ pb_status pb_set_pointer_mode(pb_context* ctx, int mode) {
 }
 pb_status pb_synchronize(pb_context* ctx) {
     return guard([&] { need(ctx, "ctx is NULL"); ctx->c.bind(); pb::stream_sync(ctx->c.ex.stream); });
+}
+
+pb_status pb_profile_start(pb_context* ctx, const char* filter) {
+    return guard([&] { need(ctx, "ctx is NULL"); ctx->c.bind(); ctx->c.profiler.start(filter); });
+}
+pb_status pb_profile_stop(pb_context* ctx, char* out, int64_t cap) {
+    return guard([&] {
+        need(ctx && out && cap > 2, "bad argument");
+        ctx->c.bind();
+        pb::stream_sync(ctx->c.ex.stream);
+        std::map<std::string, std::pair<long long, double>> agg;
+        ctx->c.profiler.collect(&agg);
+        ctx->c.profiler.on = false;
+        std::string js = "[";
+        bool first = true;
+        for (auto& kv : agg) {
+            int st = 0;
+            char* dm = abi::__cxa_demangle(kv.first.c_str(), nullptr, nullptr, &st);
+            std::string nm = (st == 0 && dm) ? dm : kv.first;
+            free(dm);
+            char buf[512];
+            snprintf(buf, sizeof buf, "%s{\"name\":\"%s\",\"launches\":%lld,\"ms\":%.6f}", first ? "" : ",", nm.c_str(),
+                     kv.second.first, kv.second.second);
+            js += buf;
+            first = false;
+        }
+        js += "]";
+        if ((int64_t)js.size() + 1 > cap) throw std::invalid_argument("profile buffer too small");
+        memcpy(out, js.c_str(), js.size() + 1);
+    });
 }
 
 pb_status pb_mesh_create(pb_context* ctx, int32_t n, const int32_t* off, const int32_t* adj, const float* xyz, pb_mesh** out) {

@@ -99,6 +99,16 @@ class DeviceMesh:
     def synchronize(self):
         self.lib.check(self.lib.dll.pb_synchronize(self._ctx))
 
+    def profile_start(self, name_filter: str | None = None):
+        f = name_filter.encode() if name_filter else None
+        self.lib.check(self.lib.dll.pb_profile_start(self._ctx, f))
+
+    def profile_stop(self) -> list:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.check(self.lib.dll.pb_profile_stop(self._ctx, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def launch_count(self) -> int:
         return int(self.lib.dll.pb_launch_count())
 
