@@ -206,6 +206,60 @@ struct Mesh {
         if (src != elev) dev_copy(elev, src, sizeof(float) * (size_t)N, 2, ex().stream);
     }
 
+#if PB_CUDA
+    // pass 1 on one CTA: shared-memory heap + visited bitmap (pb_flood.h)
+    DevBuf<HeapEntry> heapSpill;
+    DevBuf<int> liftUp, liftDepthA, liftDepthB;
+    int floodSmemMax = -1;
+    void flood_heap_cuda(const float* elev) {
+        const Exec& x = ex();
+        if (floodSmemMax < 0) {
+            int dev = 0, v = 0;
+            PB_CUDA_CHECK(cudaGetDevice(&dev));
+            PB_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            floodSmemMax = v - 2048;    // static shared + reserve
+            PB_CUDA_CHECK(cudaFuncSetAttribute(k_flood_heap, cudaFuncAttributeMaxDynamicSharedMemorySize, floodSmemMax));
+        }
+        // bitmap only when it leaves at least 64 KiB of heap in shared memory
+        int visWords = (N + 31) / 32;
+        if ((size_t)visWords * 4 + 65536 > (size_t)floodSmemMax) visWords = 0;
+        const size_t visBytes = ((size_t)visWords * 4 + 15) & ~(size_t)15;
+        const int cap = (int)((floodSmemMax - visBytes) / sizeof(HeapEntry)) - 2;
+        FloodHeapArgs a{csr(), elev, surface.p, drainTo.p, visited.p, seeds.p, counters.p + 0,
+                        heapSpill.ensure(N), cap & ~1, visWords, counters.p + 12};
+        launch_stats().launches++;
+        ProfScope ps(x.prof, "pb::k_flood_heap", x.stream);
+        k_flood_heap<<<1, PB_FLOOD_THREADS, floodSmemMax, x.stream>>>(a);
+        PB_CUDA_CHECK(cudaGetLastError());
+    }
+    // pass 2: binary lifting over the flood forest, one CTA per flood tree (pb_flood.h)
+    void carve_lift_cuda(float* elev, const uint8_t* isOcean, double carveStrength) {
+        const Exec& x = ex();
+        int maxLevels = 1; while ((1ll << maxLevels) < (long long)N && maxLevels < 16) maxLevels++;
+        liftUp.ensure((size_t)maxLevels * N); liftDepthA.ensure(N); liftDepthB.ensure(N);
+        x.for_each(N, LiftInitK{isOcean, drainTo.p, liftUp.p, liftDepthA.p});
+        int* dIn = liftDepthA.p; int* dOut = liftDepthB.p;
+        int levels = 1;
+        for (;;) {
+            if (levels >= maxLevels) throw Error("flood forest deeper than 2^16 hops");
+            dev_memset(counters.p + 13, 0, sizeof(int), x.stream);
+            x.for_each(N, LiftStepK{liftUp.p + (size_t)(levels - 1) * N, liftUp.p + (size_t)levels * N, dIn, dOut, counters.p + 13});
+            std::swap(dIn, dOut);
+            const int any = read_int(counters.p + 13);
+            if (!any) break;
+            levels++;
+        }
+        const int nSeg = read_int(counters.p + 2);
+        if (nSeg <= 0) return;
+        CarveLiftArgs a{cells.p, segStart.p, counters.p + 2, counters.p + 1, isOcean, surface.p, elev,
+                        liftUp.p, levels, N, dIn, carveStrength};
+        launch_stats().launches++;
+        ProfScope ps(x.prof, "pb::k_carve_lift", x.stream);
+        k_carve_lift<<<nSeg, PB_CARVE_THREADS, 0, x.stream>>>(a);
+        PB_CUDA_CHECK(cudaGetLastError());
+    }
+#endif
+
     // ---- priorityFloodCarve :59-215 -------------------------------------------------------------------
     void priority_flood_carve(float* elev, const uint8_t* isOcean, double carveStrength, const FloodTaps* taps) {
         const Exec& x = ex();
@@ -223,7 +277,11 @@ struct Mesh {
         counters.ensure(16);
         seeds.ensure(N); heap.ensure(N);
         prims.compact_flagged(x, seedFlag.p, N, seeds.p, counters.p + 0);
+#if PB_CUDA
+        flood_heap_cuda(elev);
+#else
         x.single(FloodSerialK{g, elev, surface.p, key.p, drainTo.p, visited.p, seeds.p, counters.p + 0, heap.p});
+#endif
         if (taps) {
             if (taps->drainTo) dev_copy(taps->drainTo, drainTo.p, sizeof(int) * (size_t)N, 2, x.stream);
             if (taps->surface) dev_copy(taps->surface, surface.p, sizeof(float) * (size_t)N, 2, x.stream);
@@ -243,7 +301,11 @@ struct Mesh {
             prims.sort_pairs(x, keys32.p, cells.p, nCells, false, bits);
             x.for_each(nCells, SegStartFlagK{(const int*)keys32.p, flag8b.p});
             prims.compact_flagged(x, flag8b.p, nCells, segStart.p, counters.p + 2);
+#if PB_CUDA
+            carve_lift_cuda(elev, isOcean, carveStrength);
+#else
             x.for_each(nCells, CarveTreeK{cells.p, segStart.p, counters.p + 2, counters.p + 1, isOcean, drainTo.p, surface.p, elev, carveStrength});
+#endif
         }
 
         // pass 3

@@ -268,3 +268,299 @@ struct EnforceK {
 };
 
 }  // namespace pb
+
+// =================================================================================================
+// CUDA-only fast forms of the two serial passes.  Same results as FloodSerialK / CarveTreeK above
+// (which remain the PB_EMUL forms and document the sequential semantics).
+// =================================================================================================
+#if PB_CUDA
+namespace pb {
+
+// ---- (1) heap flood: one CTA --------------------------------------------------------------------
+// The reference's binary MinHeap has to be replayed operation by operation (ties between equal f32
+// keys are resolved by heap layout), so pass 1 is one serial chain of ~|land| pops.
+// What can be done is to make every link of the chain cheap:
+//   * the heap lives in shared memory as (key, cell) pairs — keys never change once pushed, so the
+//     inline copy is exact and a sift step is one 16-byte LDS (both children) instead of four
+//     dependent L2 round trips; entries beyond the shared-memory capacity spill to global memory;
+//   * the visited flags live in a shared-memory bitmap when N allows;
+//   * warp 0 replays the heap; its 32 lanes expand the popped cell's neighbours in parallel and the
+//     row / surface loads of the popped cell are issued before the sift-down so they overlap it;
+//   * the other warps keep the CSR rows and neighbour elevations of the current heap top resident
+//     in L1 (plain read-only prefetching; they never write).
+struct HeapEntry { uint32_t k; int c; };   // k = __float_as_uint(key); keys compare as floats
+
+struct FloodHeapArgs {
+    Csr g; const float* elev; float* surface; int* drainTo; uint8_t* visited;
+    const int* seeds; const int* nSeeds; HeapEntry* spill; int cap; int visWords;   // visWords = 0 → visited[] in global
+    int* maxHeap;
+};
+
+#define PB_FLOOD_THREADS 128
+
+__device__ __forceinline__ HeapEntry heap_ld(const HeapEntry* sh, HeapEntry* spill, int cap, int i) {
+    if (i < cap) return sh[i + 1];
+    HeapEntry e;
+    const uint2 v = __ldcg((const uint2*)(spill + (i - cap)));
+    e.k = v.x; e.c = (int)v.y;
+    return e;
+}
+__device__ __forceinline__ void heap_st(HeapEntry* sh, HeapEntry* spill, int cap, int i, HeapEntry e) {
+    if (i < cap) sh[i + 1] = e;
+    else __stcg((uint2*)(spill + (i - cap)), make_uint2(e.k, (uint32_t)e.c));
+}
+
+__global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* vis = (uint32_t*)smem_raw;                                   // [visWords]
+    HeapEntry* sh = (HeapEntry*)(smem_raw + (((size_t)a.visWords * 4 + 15) & ~(size_t)15));   // [cap + 1], slot j+1 = node j
+    __shared__ volatile int done;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.g.N;
+    if (tid == 0) done = 0;
+    for (int w = tid; w < a.visWords; w += blockDim.x) {
+        uint32_t bits = 0;
+        const int base = w * 32;
+        for (int q = 0; q < 32; q++) if (base + q < N && a.visited[base + q]) bits |= 1u << q;
+        vis[w] = bits;
+    }
+    for (int w = tid; w < 64; w += blockDim.x) sh[w].c = 0;                  // helpers may peek before the first push
+    __syncthreads();
+
+    if (warp != 0) {
+        // ---- prefetch helpers: keep the rows of the heap's top entries hot in L1 -------------------
+        const int nHelpers = (blockDim.x >> 5) - 1;
+        while (!done) {
+            for (int idx = warp - 1; idx < 15; idx += nHelpers) {
+                int c = ((volatile HeapEntry*)sh)[idx + 1].c;
+                if (c < 0 || c >= N) continue;
+                const int b = __ldg(a.g.off + c), e = __ldg(a.g.off + c + 1);
+                if (lane < e - b && e - b <= 32) {
+                    const int nb = __ldg(a.g.adj + b + lane);
+                    if (nb >= 0 && nb < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
+                }
+            }
+            __nanosleep(64);
+        }
+        return;
+    }
+
+    // ---- warp 0: the heap engine (all lanes run the heap operations redundantly) --------------------
+    const int cap = a.cap;
+    HeapEntry* spill = a.spill;
+    int n = 0, maxN = 0;
+    auto push = [&](uint32_t kbits, int cell) {
+        int i = n++;
+        const float kc = __uint_as_float(kbits);
+        while (i > 0) {
+            const int p = (i - 1) >> 1;
+            const HeapEntry pe = heap_ld(sh, spill, cap, p);
+            if (kc >= __uint_as_float(pe.k)) break;
+            heap_st(sh, spill, cap, i, pe);
+            i = p;
+        }
+        HeapEntry me; me.k = kbits; me.c = cell;
+        heap_st(sh, spill, cap, i, me);
+    };
+    const int ns = *a.nSeeds;
+    for (int s = 0; s < ns; s++) {
+        const int c = a.seeds[s];
+        const float k = (float)((double)__ldg(a.elev + c) + cell_noise(c));
+        push(__float_as_uint(k), c);
+    }
+    __syncwarp();
+    while (n > 0) {
+        if (n > maxN) maxN = n;
+        const HeapEntry top = heap_ld(sh, spill, cap, 0);
+        const int r = top.c;
+        // issue the loads the expansion needs; they complete while the sift-down runs
+        const int b = __ldg(a.g.off + r), e = __ldg(a.g.off + r + 1);
+        const float surfRf = __ldcg(a.surface + r);
+        // pop
+        const HeapEntry last = heap_ld(sh, spill, cap, --n);
+        if (n > 0) {
+            const float kl = __uint_as_float(last.k);
+            int i = 0;
+            for (;;) {
+                const int l = 2 * i + 1;
+                if (l >= n) break;
+                HeapEntry le, re;
+                if (l + 1 < cap) {                              // both children in shared memory: one 16-byte load
+                    const uint4 v = *(const uint4*)(sh + l + 1);
+                    le.k = v.x; le.c = (int)v.y; re.k = v.z; re.c = (int)v.w;
+                } else {
+                    le = heap_ld(sh, spill, cap, l);
+                    re = (l + 1 < n) ? heap_ld(sh, spill, cap, l + 1) : le;
+                }
+                int smallest = i; float ks = kl; HeapEntry se = last;
+                if (__uint_as_float(le.k) < ks) { smallest = l; ks = __uint_as_float(le.k); se = le; }
+                if (l + 1 < n && __uint_as_float(re.k) < ks) { smallest = l + 1; se = re; }
+                if (smallest == i) break;
+                heap_st(sh, spill, cap, i, se);
+                i = smallest;
+            }
+            heap_st(sh, spill, cap, i, last);
+        }
+        __syncwarp();
+        // expand r: lane j owns neighbour j
+        const double surfR = (double)surfRf;
+        int nb = -1; uint32_t kbits = 0; bool fresh = false;
+        if (b + lane < e) {
+            nb = __ldg(a.g.adj + b + lane);
+            bool v;
+            if (a.visWords) v = (vis[nb >> 5] >> (nb & 31)) & 1u;
+            else v = __ldcg(a.visited + nb) != 0;
+            if (!v) {
+                fresh = true;
+                const float el = __ldg(a.elev + nb);
+                float s = el;
+                if ((double)el < surfR + PB_FLOOD_EPS) { s = (float)(surfR + PB_FLOOD_EPS); __stcg(a.surface + nb, s); }
+                kbits = __float_as_uint((float)((double)s + cell_noise(nb)));
+                __stcg(a.drainTo + nb, r);
+                if (a.visWords) atomicOr(vis + (nb >> 5), 1u << (nb & 31));
+                else __stcg(a.visited + nb, (uint8_t)1);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, fresh);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t kk = __shfl_sync(0xffffffffu, kbits, src);
+            const int cc = __shfl_sync(0xffffffffu, nb, src);
+            push(kk, cc);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { done = 1; if (a.maxHeap) *a.maxHeap = maxN; }
+}
+
+// ---- (2) carve: binary lifting over the flood forest, one CTA per flood tree ---------------------------
+// up[0][c] = drainTo[c] when both c and its target are flooded land, else -1; up[k] = up[k-1]∘up[k-1];
+// depth[c] = hops to the tree root (the coastal seed).  Built by pointer doubling.
+struct LiftInitK {
+    const uint8_t* isOcean; const int* drainTo; int* up0; int* depth;
+    PB_DEV void operator()(int c) const {
+        int p = -1;
+        if (!isOcean[c]) { const int t = drainTo[c]; if (t >= 0 && !isOcean[t]) p = t; }
+        up0[c] = p; depth[c] = p >= 0 ? 1 : 0;
+    }
+};
+struct LiftStepK {   // level k from level k-1; depthIn/depthOut ping-pong; *any set when some 2^k-th ancestor exists
+    const int* upPrev; int* upNext; const int* depthIn; int* depthOut; int* any;
+    PB_DEV void operator()(int c) const {
+        const int p = upPrev[c];
+        int q = -1, d = depthIn[c];
+        if (p >= 0) { q = upPrev[p]; d += depthIn[p]; if (q >= 0) *any = 1; }
+        upNext[c] = q; depthOut[c] = d;
+    }
+};
+
+struct CarveLiftArgs {
+    const int* cells; const int* segStart; const int* nSeg; const int* nCells;
+    const uint8_t* isOcean; const float* surface; float* elev;
+    const int* up; int levels; int N; const int* depth; double carveStrength;
+};
+#define PB_CARVE_THREADS 256
+
+__device__ __forceinline__ int lift_ancestor(const int* up, int N, int c, int j) {
+    for (int k = 0; j; k++, j >>= 1) if (j & 1) c = __ldg(up + (size_t)k * N + c);
+    return c;
+}
+
+__global__ void __launch_bounds__(PB_CARVE_THREADS) k_carve_lift(CarveLiftArgs a) {
+    const int s = blockIdx.x;
+    if (s >= *a.nSeg) return;
+    const int segB = a.segStart[s];
+    const int segE = (s + 1 < *a.nSeg) ? a.segStart[s + 1] : *a.nCells;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int sFirst;
+    __shared__ double sRedH[PB_CARVE_THREADS / 32];
+    __shared__ int sRedJ[PB_CARVE_THREADS / 32];
+    __shared__ double sTerm[PB_CARVE_THREADS];
+    __shared__ double sKernelSum;
+    int q0 = segB;
+    while (q0 < segE) {
+        // find the next cell (ascending id) whose current deficit exceeds EPS
+        if (tid == 0) sFirst = 0x7fffffff;
+        __syncthreads();
+        {
+            const int q = q0 + tid;
+            if (q < segE) {
+                const int r = a.cells[q];
+                const double deficit = (double)__ldg(a.surface + r) - (double)__ldcg(a.elev + r);
+                if (deficit > PB_FLOOD_EPS) atomicMin(&sFirst, q);
+            }
+        }
+        __syncthreads();
+        const int qf = sFirst;
+        if (qf == 0x7fffffff) { q0 += PB_CARVE_THREADS; __syncthreads(); continue; }
+        const int r = a.cells[qf];
+        const double deficit = (double)__ldg(a.surface + r) - (double)__ldcg(a.elev + r);
+        const int len = a.depth[r] + 1;
+        // peak = first maximum along the path (strict >)
+        double bh = -INFINITY; int bj = 0x7fffffff;
+        for (int j = tid; j < len; j += PB_CARVE_THREADS) {
+            const int c = lift_ancestor(a.up, a.N, r, j);
+            const double h = (double)__ldcg(a.elev + c);
+            if (h > bh) { bh = h; bj = j; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const double oh = __shfl_down_sync(0xffffffffu, bh, o);
+            const int oj = __shfl_down_sync(0xffffffffu, bj, o);
+            if (oh > bh || (oh == bh && oj < bj)) { bh = oh; bj = oj; }
+        }
+        if (lane == 0) { sRedH[warp] = bh; sRedJ[warp] = bj; }
+        __syncthreads();
+        int peakIdx;
+        {
+            double h = sRedH[0]; int j = sRedJ[0];
+            for (int w = 1; w < PB_CARVE_THREADS / 32; w++)
+                if (sRedH[w] > h || (sRedH[w] == h && sRedJ[w] < j)) { h = sRedH[w]; j = sRedJ[w]; }
+            peakIdx = j;
+        }
+        if (peakIdx == 0x7fffffff) { q0 = qf + 1; __syncthreads(); continue; }   // all-NaN path: reference skips the cell
+        const double carveAmount = deficit * a.carveStrength;
+        double rad = ceil(len * 0.3);
+        if (rad < 3) rad = 3;
+        const int radius = (int)rad;
+        const int startIdx = peakIdx - radius > 0 ? peakIdx - radius : 0;
+        const int endIdx = peakIdx + radius < len - 1 ? peakIdx + radius : len - 1;
+        // kernelSum is a sequential double sum in the reference: terms in parallel, sum by one thread
+        double ksum = 0;
+        for (int base = startIdx; base <= endIdx; base += PB_CARVE_THREADS) {
+            const int k = base + tid;
+            if (k <= endIdx) {
+                const double dist = k > peakIdx ? k - peakIdx : peakIdx - k;
+                sTerm[tid] = 1 - dist / (radius + 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int cnt = endIdx - base + 1 < PB_CARVE_THREADS ? endIdx - base + 1 : PB_CARVE_THREADS;
+                for (int t = 0; t < cnt; t++) ksum += sTerm[t];
+                sKernelSum = ksum;
+            }
+            __syncthreads();
+        }
+        const double kernelSum = sKernelSum;
+        if (kernelSum > 0) {
+            for (int k = startIdx + tid; k <= endIdx; k += PB_CARVE_THREADS) {
+                const int c = lift_ancestor(a.up, a.N, r, k);
+                const double dist = k > peakIdx ? k - peakIdx : peakIdx - k;
+                const double weight = (1 - dist / (radius + 1)) / kernelSum;
+                float v = (float)((double)__ldcg(a.elev + c) - carveAmount * weight);
+                if (v < 0) v = 0;
+                __stcg(a.elev + c, v);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double fillAmount = deficit * (1 - a.carveStrength);
+            __stcg(a.elev + r, (float)((double)__ldcg(a.elev + r) + fillAmount));
+        }
+        __syncthreads();
+        q0 = qf + 1;
+    }
+}
+
+}  // namespace pb
+#endif  // PB_CUDA

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <typeinfo>
 #include <map>
+#include <cxxabi.h>
 
 #if defined(__CUDACC__) && !defined(PB_EMUL)
 #define PB_CUDA 1
@@ -178,7 +179,18 @@ struct Profiler {
         for (auto e : pool) cudaEventDestroy(e);
     }
 #endif
-    bool wants(const char* name) const { return on && (filter.empty() || strstr(name, filter.c_str()) != nullptr); }
+    // launch names are typeid names (mangled) or plain strings; the filter is matched on the readable form
+    std::map<const char*, std::string> readable;
+    const std::string& pretty(const char* name) {
+        auto it = readable.find(name);
+        if (it != readable.end()) return it->second;
+        int st = 0;
+        char* dm = abi::__cxa_demangle(name, nullptr, nullptr, &st);
+        std::string out = (st == 0 && dm) ? dm : name;
+        free(dm);
+        return readable[name] = out;
+    }
+    bool wants(const char* name) { return on && (filter.empty() || pretty(name).find(filter) != std::string::npos); }
     void start(const char* f) {
         collect(nullptr);
         filter = f ? f : "";

@@ -71,6 +71,22 @@ def test_priority_flood_carve(backend, oracle, planet_medium, strength):
     assert_bit_equal(got, want, "priorityFloodCarve elevation")
 
 
+@pytest.mark.gpu
+def test_priority_flood_carve_large(oracle, cuda_lib):
+    """250k cells: deep flood trees (hundreds of hops), thousands of filled cells, a heap of thousands of entries."""
+    from planet_heightmap_generation_b200.terrain_post import priorityFloodCarve
+    from tests.conftest import make_planet
+    mesh, xyz, nd, elev = make_planet(oracle, 250000)
+    ocean = (elev <= 0).astype(np.uint8)
+    want = elev.copy()
+    o_drain, o_surf, o_open = oracle.priority_flood_carve(mesh, want, ocean, 0.85)
+    got = elev.copy()
+    drain, surf, openo = priorityFloodCarve(_dm(cuda_lib, mesh, xyz), got, ocean, 0.85, taps=True)
+    assert_bit_equal(drain, o_drain, "drainTo")
+    assert_bit_equal(surf, o_surf, "surface")
+    assert_bit_equal(got, want, "priorityFloodCarve elevation")
+
+
 def test_flood_with_inland_sea_and_island(backend, oracle, planet_small):
     """Second-largest ocean component is an inland sea (not a flood seed); an island inside it is never flooded."""
     from planet_heightmap_generation_b200.terrain_post import priorityFloodCarve
