@@ -136,6 +136,49 @@ pb_status pb_last_post_timing(pb_mesh* mesh, double* ms_out);
 /* smoothField(mesh, field, passes)                                    js/climate-util.js:5-25 */
 pb_status pb_smooth_field(pb_mesh* mesh, float* field, int32_t passes);
 
+/* ---- climate (js/wind.js, js/ocean.js, js/precipitation.js, js/heuristic-precip.js, js/temperature.js,
+ * js/koppen.js) ------------------------------------------------------------------------------------------
+ * A pb_climate holds the reference's result objects (windResult, oceanResult, precipResult, tempResult —
+ * what the worker retains as W.cachedWind / W.cachedOcean, js/planet-worker.js:291, 588-606) resident in
+ * HBM.  Stages must run in the reference's order (js/planet-worker.js:229-268); a stage called before its
+ * inputs exist fails with PB_ERR_INVALID, like the reference throws on an undefined result object.
+ * Fields are read back by the reference's own key names with pb_climate_get:
+ *   wind   r_lat r_lon r_sinLat r_cosLat r_eastX/Y/Z r_northX/Y/Z r_continentality r_plateContinentality
+ *          r_pressure_<s> r_wind_east_<s> r_wind_north_<s> r_wind_speed_<s> itczLons itczLatsSummer
+ *          itczLatsWinter (f32; the ITCZ tables have 360 entries), r_isLand (u8), r_coastDistLand (i32)
+ *   ocean  r_ocean_current_east_<s> r_ocean_current_north_<s> r_ocean_speed_<s> r_ocean_warmth_<s> (f32),
+ *          r_oceanCoastDist r_westCoastDist r_eastCoastDist (i32; locals of computeCoastFields)
+ *   precip r_precip_<s> r_rainshadow_<s> (f32)        temperature r_temperature_<s> (f32)
+ *   koppen r_koppen (u8)                                <s> = summer | winter
+ * r_elevation / r_plate follow the context's pointer mode; plateIsOcean is always a host array of plate ids
+ * (the reference passes a Set, js/wind.js:394). */
+typedef struct pb_climate pb_climate;
+pb_status pb_climate_create(pb_mesh* mesh, pb_climate** out);
+void pb_climate_destroy(pb_climate* climate);
+/* computeWind(mesh, r_xyz, r_elevation, plateIsOcean, r_plate, noise, axialTilt)        js/wind.js:394-687
+ * `noiseSeed` seeds the SimplexNoise instance the worker passes (new SimplexNoise(seed), planet-worker.js:203). */
+pb_status pb_compute_wind(pb_climate* climate, const float* r_elevation, const int32_t* plateIsOcean,
+                          int32_t numPlateIsOcean, const int32_t* r_plate, double noiseSeed, double axialTilt);
+/* computeOceanCurrents(mesh, r_xyz, r_elevation, windResult)                            js/ocean.js:204-382 */
+pb_status pb_compute_ocean_currents(pb_climate* climate, const float* r_elevation);
+/* computePrecipitation(mesh, r_xyz, r_elevation, windResult, oceanResult, precipitationOffset, landCoverage)
+ *                                                                              js/precipitation.js:196-684 */
+pb_status pb_compute_precipitation(pb_climate* climate, const float* r_elevation, double precipitationOffset,
+                                   double landCoverage);
+/* computeTemperature(mesh, r_xyz, r_elevation, windResult, oceanResult, precipResult, temperatureOffset)
+ *                                                                                js/temperature.js:69-237 */
+pb_status pb_compute_temperature(pb_climate* climate, const float* r_elevation, double temperatureOffset);
+/* classifyKoppen(mesh, r_elevation, tempResult, precipResult) → Uint8Array             js/koppen.js:67-288 */
+pb_status pb_classify_koppen(pb_climate* climate, const float* r_elevation, uint8_t* r_koppen_out);
+/* handleComputeClimate without the cache: all five stages                     js/planet-worker.js:579-672 */
+pb_status pb_compute_climate(pb_climate* climate, const float* r_elevation, const int32_t* plateIsOcean,
+                             int32_t numPlateIsOcean, const int32_t* r_plate, double noiseSeed,
+                             double temperatureOffset, double precipitationOffset, double landCoverage,
+                             uint8_t* r_koppen_out);
+/* kind: 0 float32, 1 int32, 2 uint8.  PB_ERR_INVALID when the field does not exist (yet). */
+pb_status pb_climate_field_info(pb_climate* climate, const char* name, int32_t* kind_out, int64_t* count_out);
+pb_status pb_climate_get(pb_climate* climate, const char* name, void* out);
+
 #ifdef __cplusplus
 }
 #endif

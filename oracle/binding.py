@@ -22,8 +22,9 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+    if force and os.path.exists(so):
+        os.unlink(so)
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])   # no-op when up to date
     return so
 
 
@@ -34,6 +35,8 @@ def lib():
         _LIB.orc_cell_noise.restype = C.c_double
         _LIB.orc_cell_noise.argtypes = [C.c_double]
         _LIB.orc_percentile.restype = C.c_double
+        _LIB.orc_climate_create.restype = C.c_void_p
+        _LIB.orc_climate_get.restype = C.c_int64
     return _LIB
 
 
@@ -167,3 +170,76 @@ def smooth_field(mesh, field, passes):
 def percentile(arr, p):
     arr = np.ascontiguousarray(arr, np.float32)
     return lib().orc_percentile(_p(arr, C.c_float), C.c_int(arr.size), C.c_double(p))
+
+
+# ---- climate stack (oracle/climate.cpp) ---------------------------------------------------------------
+_KIND = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.uint8): 2}
+
+
+class Climate:
+    """computeWind → computeOceanCurrents → computePrecipitation → computeTemperature → classifyKoppen
+    (js/planet-worker.js:229-268) with every result field kept under the reference's key name."""
+
+    def __init__(self, mesh, xyz):
+        self.mesh = mesh
+        self.xyz = np.ascontiguousarray(xyz, np.float32)
+        self._off = np.ascontiguousarray(mesh.adjOffset, np.int32)
+        self._adj = np.ascontiguousarray(mesh.adjList, np.int32)
+        self._h = C.c_void_p(lib().orc_climate_create(C.c_int(mesh.numRegions), _p(self._off, C.c_int32),
+                                                      _p(self._adj, C.c_int32), _p(self.xyz, C.c_float)))
+
+    def __del__(self):
+        try:
+            lib().orc_climate_destroy(self._h)
+        except Exception:
+            pass
+
+    def wind(self, elev, plate_is_ocean, r_plate, noise_seed, axial_tilt=23.5):
+        ids = np.ascontiguousarray(sorted(plate_is_ocean), np.int32)
+        r_plate = np.ascontiguousarray(r_plate, np.int32)
+        lib().orc_climate_wind(self._h, _p(elev, C.c_float), _p(ids, C.c_int32), C.c_int(ids.size),
+                               _p(r_plate, C.c_int32), C.c_double(noise_seed), C.c_double(axial_tilt))
+
+    def ocean(self, elev):
+        lib().orc_climate_ocean(self._h, _p(elev, C.c_float))
+
+    def precipitation(self, elev, precipitation_offset=0.0, land_coverage=0.3):
+        lib().orc_climate_precip(self._h, _p(elev, C.c_float), C.c_double(precipitation_offset),
+                                 C.c_double(land_coverage))
+
+    def temperature(self, elev, temperature_offset=0.0):
+        lib().orc_climate_temperature(self._h, _p(elev, C.c_float), C.c_double(temperature_offset))
+
+    def koppen(self, elev):
+        lib().orc_climate_koppen(self._h, _p(elev, C.c_float))
+        return self.get("r_koppen", np.uint8)
+
+    def run_all(self, elev, plate_is_ocean, r_plate, noise_seed, temperature_offset=0.0, precipitation_offset=0.0,
+                land_coverage=0.3):
+        self.wind(elev, plate_is_ocean, r_plate, noise_seed)
+        self.ocean(elev)
+        self.precipitation(elev, precipitation_offset, land_coverage)
+        self.temperature(elev, temperature_offset)
+        return self.koppen(elev)
+
+    def get(self, name, dtype=np.float32):
+        kind = _KIND[np.dtype(dtype)]
+        n = lib().orc_climate_get(self._h, name.encode(), C.c_int(kind), None, C.c_int64(0))
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype)
+        lib().orc_climate_get(self._h, name.encode(), C.c_int(kind), out.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return out
+
+
+def compute_gradients(mesh, xyz, field, frames6):
+    n = mesh.numRegions
+    frames6 = np.ascontiguousarray(frames6, np.float32)
+    ge, gn = np.empty(n, np.float32), np.empty(n, np.float32)
+    lib().orc_compute_gradients(*_mesh_args(mesh), _p(xyz, C.c_float), _p(field, C.c_float), _p(frames6, C.c_float),
+                                _p(ge, C.c_float), _p(gn, C.c_float))
+    return ge, gn
+
+
+def smooth_masked(mesh, field, mask, passes):
+    lib().orc_smooth_masked(*_mesh_args(mesh), _p(field, C.c_float), _p(mask, C.c_uint8), C.c_int(passes))

@@ -54,6 +54,16 @@ SYMBOLS = {
     "pb_run_post_processing": (C.c_int, [_vp, _vp, C.POINTER(PostParams), _dbl, _vp, _vp, _vp]),
     "pb_last_post_timing": (C.c_int, [_vp, _vp]),
     "pb_smooth_field": (C.c_int, [_vp, _vp, _i32]),
+    "pb_climate_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "pb_climate_destroy": (None, [_vp]),
+    "pb_compute_wind": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _dbl, _dbl]),
+    "pb_compute_ocean_currents": (C.c_int, [_vp, _vp]),
+    "pb_compute_precipitation": (C.c_int, [_vp, _vp, _dbl, _dbl]),
+    "pb_compute_temperature": (C.c_int, [_vp, _vp, _dbl]),
+    "pb_classify_koppen": (C.c_int, [_vp, _vp, _vp]),
+    "pb_compute_climate": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
+    "pb_climate_field_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32), C.POINTER(_i64)]),
+    "pb_climate_get": (C.c_int, [_vp, C.c_char_p, _vp]),
 }
 
 

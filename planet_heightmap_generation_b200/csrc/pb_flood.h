@@ -283,7 +283,6 @@ namespace pb {
 //   * the heap lives in shared memory as (key, cell) pairs — keys never change once pushed, so the
 //     inline copy is exact and a sift step is one 16-byte LDS (both children) instead of four
 //     dependent L2 round trips; entries beyond the shared-memory capacity spill to global memory;
-//   * the visited flags live in a shared-memory bitmap when N allows;
 //   * warp 0 replays the heap; its 32 lanes expand the popped cell's neighbours in parallel and the
 //     row / surface loads of the popped cell are issued before the sift-down so they overlap it;
 //   * the other warps keep the CSR rows and neighbour elevations of the current heap top resident
@@ -292,38 +291,44 @@ struct HeapEntry { uint32_t k; int c; };   // k = __float_as_uint(key); keys com
 
 struct FloodHeapArgs {
     Csr g; const float* elev; float* surface; int* drainTo; uint8_t* visited;
-    const int* seeds; const int* nSeeds; HeapEntry* spill; int cap; int visWords;   // visWords = 0 → visited[] in global
-    int* maxHeap;
+    const int* seeds; const int* nSeeds; HeapEntry* spill; int cap;
+    int* status;   // [0] max heap size reached, [1] set to 1 when the no-spill variant ran out of shared memory
 };
 
 #define PB_FLOOD_THREADS 128
 
-__device__ __forceinline__ HeapEntry heap_ld(const HeapEntry* sh, HeapEntry* spill, int cap, int i) {
-    if (i < cap) return sh[i + 1];
-    HeapEntry e;
-    const uint2 v = __ldcg((const uint2*)(spill + (i - cap)));
-    e.k = v.x; e.c = (int)v.y;
-    return e;
-}
-__device__ __forceinline__ void heap_st(HeapEntry* sh, HeapEntry* spill, int cap, int i, HeapEntry e) {
-    if (i < cap) sh[i + 1] = e;
-    else __stcg((uint2*)(spill + (i - cap)), make_uint2(e.k, (uint32_t)e.c));
-}
+// Heap storage: node j lives in slot j+1 of the shared array, so the two children of a node share
+// one aligned 16-byte word.  SPILL adds a global-memory tail for nodes >= cap.
+template <bool SPILL>
+struct HeapStore {
+    HeapEntry* sh; HeapEntry* spill; int cap;
+    __device__ __forceinline__ HeapEntry ld(int i) const {
+        if (!SPILL || i < cap) return sh[i + 1];
+        const uint2 v = __ldcg((const uint2*)(spill + (i - cap)));
+        HeapEntry e; e.k = v.x; e.c = (int)v.y;
+        return e;
+    }
+    __device__ __forceinline__ void st(int i, HeapEntry e) const {
+        if (!SPILL || i < cap) sh[i + 1] = e;
+        else __stcg((uint2*)(spill + (i - cap)), make_uint2(e.k, (uint32_t)e.c));
+    }
+    // children l and l+1 of a node; the right one may be beyond n (caller checks)
+    __device__ __forceinline__ void ld2(int l, HeapEntry& le, HeapEntry& re) const {
+        if (!SPILL || l + 1 < cap) {
+            const uint4 v = *(const uint4*)(sh + l + 1);
+            le.k = v.x; le.c = (int)v.y; re.k = v.z; re.c = (int)v.w;
+        } else { le = ld(l); re = ld(l + 1); }
+    }
+};
 
+template <bool SPILL>
 __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* vis = (uint32_t*)smem_raw;                                   // [visWords]
-    HeapEntry* sh = (HeapEntry*)(smem_raw + (((size_t)a.visWords * 4 + 15) & ~(size_t)15));   // [cap + 1], slot j+1 = node j
+    HeapEntry* sh = (HeapEntry*)smem_raw;                                  // [cap + 2]
     __shared__ volatile int done;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.g.N;
     if (tid == 0) done = 0;
-    for (int w = tid; w < a.visWords; w += blockDim.x) {
-        uint32_t bits = 0;
-        const int base = w * 32;
-        for (int q = 0; q < 32; q++) if (base + q < N && a.visited[base + q]) bits |= 1u << q;
-        vis[w] = bits;
-    }
     for (int w = tid; w < 64; w += blockDim.x) sh[w].c = 0;                  // helpers may peek before the first push
     __syncthreads();
 
@@ -340,44 +345,49 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                     if (nb >= 0 && nb < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
                 }
             }
-            __nanosleep(64);
+            __nanosleep(100);
         }
         return;
     }
 
-    // ---- warp 0: the heap engine (all lanes run the heap operations redundantly) --------------------
-    const int cap = a.cap;
-    HeapEntry* spill = a.spill;
+    // ---- warp 0: the heap engine.  All 32 lanes run the heap operations redundantly (same addresses,
+    // same values), which keeps the warp converged; a single warp issues dependent instructions at
+    // roughly one per 4-6 cycles, so the loops below are written for the fewest instructions per level.
+    const HeapStore<SPILL> H{sh, a.spill, a.cap};
     int n = 0, maxN = 0;
+    bool overflow = false;
     auto push = [&](uint32_t kbits, int cell) {
         int i = n++;
         const float kc = __uint_as_float(kbits);
         while (i > 0) {
             const int p = (i - 1) >> 1;
-            const HeapEntry pe = heap_ld(sh, spill, cap, p);
-            if (kc >= __uint_as_float(pe.k)) break;
-            heap_st(sh, spill, cap, i, pe);
+            const HeapEntry pe = H.ld(p);
+            if (kc >= __uint_as_float(pe.k)) break;          // MinHeap.push stops on >=   (:22)
+            H.st(i, pe);
             i = p;
         }
         HeapEntry me; me.k = kbits; me.c = cell;
-        heap_st(sh, spill, cap, i, me);
+        H.st(i, me);
     };
     const int ns = *a.nSeeds;
-    for (int s = 0; s < ns; s++) {
+    if (!SPILL && ns + 64 > a.cap) overflow = true;
+    for (int s = 0; s < ns && !overflow; s++) {
         const int c = a.seeds[s];
         const float k = (float)((double)__ldg(a.elev + c) + cell_noise(c));
         push(__float_as_uint(k), c);
     }
     __syncwarp();
-    while (n > 0) {
+    int r = n > 0 ? H.ld(0).c : -1;
+    int b = 0, e = 0;
+    float surfRf = 0.f;
+    if (r >= 0) { b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r); }
+    while (n > 0 && !overflow) {
         if (n > maxN) maxN = n;
-        const HeapEntry top = heap_ld(sh, spill, cap, 0);
-        const int r = top.c;
-        // issue the loads the expansion needs; they complete while the sift-down runs
-        const int b = __ldg(a.g.off + r), e = __ldg(a.g.off + r + 1);
-        const float surfRf = __ldcg(a.surface + r);
-        // pop
-        const HeapEntry last = heap_ld(sh, spill, cap, --n);
+        // neighbour ids of the popped cell: in flight while the sift-down runs
+        int nb = -1;
+        if (b + lane < e) nb = __ldg(a.g.adj + b + lane);
+        // pop: MinHeap.pop (:27-46) — last → root, sift down along the min-child path (left child on ties)
+        const HeapEntry last = H.ld(--n);
         if (n > 0) {
             const float kl = __uint_as_float(last.k);
             int i = 0;
@@ -385,43 +395,35 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                 const int l = 2 * i + 1;
                 if (l >= n) break;
                 HeapEntry le, re;
-                if (l + 1 < cap) {                              // both children in shared memory: one 16-byte load
-                    const uint4 v = *(const uint4*)(sh + l + 1);
-                    le.k = v.x; le.c = (int)v.y; re.k = v.z; re.c = (int)v.w;
-                } else {
-                    le = heap_ld(sh, spill, cap, l);
-                    re = (l + 1 < n) ? heap_ld(sh, spill, cap, l + 1) : le;
-                }
-                int smallest = i; float ks = kl; HeapEntry se = last;
-                if (__uint_as_float(le.k) < ks) { smallest = l; ks = __uint_as_float(le.k); se = le; }
-                if (l + 1 < n && __uint_as_float(re.k) < ks) { smallest = l + 1; se = re; }
-                if (smallest == i) break;
-                heap_st(sh, spill, cap, i, se);
-                i = smallest;
+                H.ld2(l, le, re);
+                const bool right = (l + 1 < n) && (__uint_as_float(re.k) < __uint_as_float(le.k));
+                HeapEntry m; m.k = right ? re.k : le.k; m.c = right ? re.c : le.c;
+                if (!(__uint_as_float(m.k) < kl)) break;
+                H.st(i, m);
+                i = l + (right ? 1 : 0);
             }
-            heap_st(sh, spill, cap, i, last);
+            H.st(i, last);
         }
         __syncwarp();
         // expand r: lane j owns neighbour j
         const double surfR = (double)surfRf;
-        int nb = -1; uint32_t kbits = 0; bool fresh = false;
-        if (b + lane < e) {
-            nb = __ldg(a.g.adj + b + lane);
-            bool v;
-            if (a.visWords) v = (vis[nb >> 5] >> (nb & 31)) & 1u;
-            else v = __ldcg(a.visited + nb) != 0;
+        uint32_t kbits = 0; bool fresh = false;
+        if (nb >= 0) {
+            // visited flag and elevation are fetched together (one L2 round trip on the critical path)
+            const bool v = __ldcg(a.visited + nb) != 0;
+            const float el = __ldg(a.elev + nb);
+            const double noise = cell_noise(nb);
             if (!v) {
                 fresh = true;
-                const float el = __ldg(a.elev + nb);
                 float s = el;
                 if ((double)el < surfR + PB_FLOOD_EPS) { s = (float)(surfR + PB_FLOOD_EPS); __stcg(a.surface + nb, s); }
-                kbits = __float_as_uint((float)((double)s + cell_noise(nb)));
+                kbits = __float_as_uint((float)((double)s + noise));
                 __stcg(a.drainTo + nb, r);
-                if (a.visWords) atomicOr(vis + (nb >> 5), 1u << (nb & 31));
-                else __stcg(a.visited + nb, (uint8_t)1);
+                __stcg(a.visited + nb, (uint8_t)1);
             }
         }
         unsigned m = __ballot_sync(0xffffffffu, fresh);
+        if (!SPILL && n + __popc(m) + 2 > a.cap) { overflow = true; break; }
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
@@ -430,8 +432,13 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
             push(kk, cc);
         }
         __syncwarp();
+        // next pop is the root now; start its row / surface loads right away
+        if (n > 0) {
+            r = H.ld(0).c;
+            b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r);
+        }
     }
-    if (lane == 0) { done = 1; if (a.maxHeap) *a.maxHeap = maxN; }
+    if (lane == 0) { done = 1; a.status[0] = maxN; if (overflow) a.status[1] = 1; }
 }
 
 // ---- (2) carve: binary lifting over the flood forest, one CTA per flood tree ---------------------------

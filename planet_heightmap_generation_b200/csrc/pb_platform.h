@@ -262,6 +262,16 @@ template <class F>
 PB_GLOBAL void k_single(F f) {
     f();
 }
+
+// grid-stride loop whose bound lives in device memory (frontier sizes); global thread 0 first runs
+// the functor's block0() hook.
+template <class F>
+PB_GLOBAL void __launch_bounds__(256) k_for_dev(F f, const int* nDev) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) f.block0();
+    const int n = *nDev;
+    for (int i = t; i < n; i += gridDim.x * blockDim.x) f(i);
+}
 #endif
 
 struct Exec {
@@ -301,6 +311,21 @@ struct Exec {
         for (int i = 0; i < n; i++) {
             if (!f.try_run(i)) throw Error("ordered dataflow: dependency of a later item (emulation)");
         }
+#endif
+    }
+
+    // f(i) for i < *nDev (device-resident bound); f.block0() runs once first
+    template <class F>
+    void for_each_dev(const int* nDev, const F& f) const {
+        launch_stats().launches++;
+        ProfScope ps(prof, typeid(F).name(), stream);
+#if PB_CUDA
+        k_for_dev<F><<<sm_count * 4, 256, 0, stream>>>(f, nDev);
+        PB_CUDA_CHECK(cudaGetLastError());
+#else
+        f.block0();
+        const int n = *nDev;
+        for (int i = 0; i < n; i++) f(i);
 #endif
     }
 

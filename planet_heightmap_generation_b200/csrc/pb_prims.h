@@ -50,6 +50,24 @@ struct Prims {
 #endif
     }
 
+    // ascending sort of unsigned 32-bit keys in place (selection / percentile)
+    void sort_keys(const Exec& ex, uint32_t* keys, int n) {
+        if (n <= 1) return;
+        launch_stats().launches++;
+        ProfScope ps(ex.prof, "cub::DeviceRadixSort::SortKeys", ex.stream);
+#if PB_CUDA
+        kAlt.ensure(n);
+        cub::DoubleBuffer<uint32_t> dk(keys, kAlt.p);
+        size_t bytes = 0;
+        PB_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, dk, n, 0, 32, ex.stream));
+        temp.ensure(bytes);
+        PB_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(temp.p, bytes, dk, n, 0, 32, ex.stream));
+        if (dk.Current() != keys) dev_copy(keys, dk.Current(), (size_t)n * sizeof(uint32_t), 2, ex.stream);
+#else
+        std::sort(keys, keys + n);
+#endif
+    }
+
     // stable sort of (key, val) pairs in place; descending or ascending on unsigned 32-bit keys
     void sort_pairs(const Exec& ex, uint32_t* keys, int* vals, int n, bool descending, int endBit = 32) {
         if (n <= 1) return;

@@ -2,6 +2,7 @@
 // Compiled by nvcc for sm_100a into libplanet_b200.so (product), or by g++ with -DPB_EMUL into the
 // test-only host emulation used by the CPU test-suite (tests/emul/).
 #include "pb_engine.h"
+#include "pb_climate_engine.h"
 #include <cxxabi.h>
 
 namespace {
@@ -33,6 +34,8 @@ struct pb_mesh {
     pb::Mesh m;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
+
+struct pb_climate { pb::Climate c; explicit pb_climate(pb::Mesh* m) : c(m) {} };
 
 extern "C" {
 
@@ -244,6 +247,82 @@ pb_status pb_last_post_timing(pb_mesh* mesh, double* ms) {
         mesh->m.ctx->bind();
         mesh->m.timer.resolve();
         for (int i = 0; i < 5; i++) ms[i] = mesh->m.timer.ms[i];
+    });
+}
+
+// ---- climate ---------------------------------------------------------------------------------------------
+pb_status pb_climate_create(pb_mesh* mesh, pb_climate** out) {
+    return guard([&] { need(mesh && out, "NULL argument"); mesh->m.ctx->bind(); *out = new pb_climate(&mesh->m); });
+}
+void pb_climate_destroy(pb_climate* c) { delete c; }
+
+#define PB_CLIMATE_PROLOGUE                                          \
+    need(climate && elev, "NULL argument");                          \
+    pb::Climate& c = climate->c; pb::Mesh& m = *c.m; m.ctx->bind();  \
+    const float* d = m.arg_in(elev, m.N, c.sElev);
+
+pb_status pb_compute_wind(pb_climate* climate, const float* elev, const int32_t* ids, int32_t nIds, const int32_t* r_plate,
+                          double noiseSeed, double axialTilt) {
+    return guard([&] {
+        PB_CLIMATE_PROLOGUE
+        need(r_plate != nullptr && (ids != nullptr || nIds == 0) && nIds >= 0, "bad plate arguments");
+        const int* p = m.arg_in(r_plate, m.N, c.sPlate);
+        c.compute_wind(d, ids, nIds, p, noiseSeed, axialTilt);
+        m.finish();
+    });
+}
+pb_status pb_compute_ocean_currents(pb_climate* climate, const float* elev) {
+    return guard([&] { PB_CLIMATE_PROLOGUE c.compute_ocean_currents(d); m.finish(); });
+}
+pb_status pb_compute_precipitation(pb_climate* climate, const float* elev, double precipitationOffset, double landCoverage) {
+    return guard([&] { PB_CLIMATE_PROLOGUE c.compute_precipitation(d, precipitationOffset, landCoverage); m.finish(); });
+}
+pb_status pb_compute_temperature(pb_climate* climate, const float* elev, double temperatureOffset) {
+    return guard([&] { PB_CLIMATE_PROLOGUE c.compute_temperature(d, temperatureOffset); m.finish(); });
+}
+pb_status pb_classify_koppen(pb_climate* climate, const float* elev, uint8_t* out) {
+    return guard([&] {
+        PB_CLIMATE_PROLOGUE
+        c.classify_koppen(d);
+        if (out) pb::dev_copy(out, c.cU("r_koppen"), (size_t)m.N, m.hostMode() ? 1 : 2, m.ex().stream);
+        m.finish();
+    });
+}
+pb_status pb_compute_climate(pb_climate* climate, const float* elev, const int32_t* ids, int32_t nIds, const int32_t* r_plate,
+                             double noiseSeed, double temperatureOffset, double precipitationOffset, double landCoverage,
+                             uint8_t* koppenOut) {
+    return guard([&] {
+        PB_CLIMATE_PROLOGUE
+        need(r_plate != nullptr && (ids != nullptr || nIds == 0) && nIds >= 0, "bad plate arguments");
+        const int* p = m.arg_in(r_plate, m.N, c.sPlate);
+        c.compute_wind(d, ids, nIds, p, noiseSeed, 23.5);
+        c.compute_ocean_currents(d);
+        c.compute_precipitation(d, precipitationOffset, landCoverage);
+        c.compute_temperature(d, temperatureOffset);
+        c.classify_koppen(d);
+        if (koppenOut) pb::dev_copy(koppenOut, c.cU("r_koppen"), (size_t)m.N, m.hostMode() ? 1 : 2, m.ex().stream);
+        m.finish();
+    });
+}
+pb_status pb_climate_field_info(pb_climate* climate, const char* name, int32_t* kind, int64_t* count) {
+    return guard([&] {
+        need(climate && name, "NULL argument");
+        auto it = climate->c.count.find(name);
+        if (it == climate->c.count.end()) throw std::invalid_argument(std::string("no such climate field: ") + name);
+        if (kind) *kind = climate->c.kind[name];
+        if (count) *count = (int64_t)it->second;
+    });
+}
+pb_status pb_climate_get(pb_climate* climate, const char* name, void* out) {
+    return guard([&] {
+        need(climate && name && out, "NULL argument");
+        pb::Climate& c = climate->c; pb::Mesh& m = *c.m; m.ctx->bind();
+        auto it = c.count.find(name);
+        if (it == c.count.end()) throw std::invalid_argument(std::string("no such climate field: ") + name);
+        const int k = c.kind[name];
+        const void* src = k == 0 ? (const void*)c.cF(name) : k == 1 ? (const void*)c.cI(name) : (const void*)c.cU(name);
+        pb::dev_copy(out, src, it->second * (k == 2 ? 1 : 4), m.hostMode() ? 1 : 2, m.ex().stream);
+        m.finish();
     });
 }
 

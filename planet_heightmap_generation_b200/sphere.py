@@ -93,3 +93,22 @@ def synthetic_elevation(r_xyz: np.ndarray, seed: int, land_fraction: float = 0.3
     land = h > 0
     h[land] = h[land] ** 0.8 * 0.9
     return h.astype(np.float32)
+
+
+def synthetic_plates(r_xyz: np.ndarray, elevation: np.ndarray, seed: int, n_plates: int = 40):
+    """Seeded stand-in for the plate pipeline's outputs that the climate stage reads: `r_plate`
+    (per-cell plate id = a cell id, like the reference's plate seeds) and `plateIsOcean` (set of plate
+    ids).  Plates are spherical Voronoi regions of random seed cells; a plate is oceanic when most of
+    its cells are below sea level, so continental shelves and inland seas exist as in the reference."""
+    p = np.asarray(r_xyz, np.float32).reshape(-1, 3)
+    rng = np.random.default_rng(seed + 7919)
+    seeds = np.sort(rng.choice(p.shape[0], size=n_plates, replace=False)).astype(np.int32)
+    owner = np.empty(p.shape[0], np.int64)
+    B = 1 << 18
+    for s0 in range(0, p.shape[0], B):
+        owner[s0:s0 + B] = np.argmax(p[s0:s0 + B] @ p[seeds].T, axis=1)
+    r_plate = seeds[owner].astype(np.int32)
+    below = np.bincount(owner, weights=(np.asarray(elevation) <= 0), minlength=n_plates)
+    size = np.bincount(owner, minlength=n_plates)
+    plate_is_ocean = {int(seeds[k]) for k in range(n_plates) if below[k] > 0.5 * size[k]}
+    return r_plate, plate_is_ocean
