@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — Voronoi cells/s of the terrain-post hot path (BASELINE.json configs[1]).
+"""bench.py — Voronoi cells/s of the per-cell hot path (BASELINE.json: full pipeline erosion→climate).
 
-A "step" is one `reapply`-style pass (js/planet-worker.js:341-358): clone the pre-erosion elevation,
-then runPostProcessing (warp → smooth → erodeComposite with 50 stream-power iterations, 5 glacial,
-1 thermal, two priority floods → ridge sharpening → soil creep → erosionDelta) over a 1 000 001-cell
-Fibonacci-sphere Voronoi mesh, seed 42, sliders at the reference's UI defaults.
+A "step" is one pass over a 1 000 001-cell Fibonacci-sphere Voronoi mesh (seed 42, sliders at the
+reference's UI defaults):
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells C]
+  --workload full (default, BASELINE configs[2]) = post + climate
+  --workload post    (configs[1])  reapply-style pass (js/planet-worker.js:341-358): clone the pre-erosion
+                     elevation, runPostProcessing = warp → smooth → erodeComposite (50 stream-power iterations,
+                     5 glacial, 1 thermal, two priority floods) → ridge sharpening → soil creep → erosionDelta
+  --workload climate computeWind → computeOceanCurrents → computePrecipitation → computeTemperature →
+                     classifyKoppen on the eroded elevation (js/planet-worker.js:229-268)
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells C] [--workload W]
 
 own arm       value  = cells/s with the planet resident in HBM (device-pointer mode of the C ABI),
                        CUDA-event timed, max over ranks; N>1 = N independent planets (replicas, weak).
-              e2e    = the same pass through the host-pointer C ABI (pinned host buffers in, results
-                       back in host memory), wall clock.
+              e2e    = the same pass through the host-pointer C ABI (pinned host buffers in, every result
+                       array of the reference's reply message back in host memory), wall clock.
               roofline / cpu_baseline as the task contract asks.
 reference arm the CPU oracle (oracle/, single thread like the reference's single Web Worker) on the
               same workload.  The reference itself is JavaScript and no JS runtime exists in this image.
@@ -35,7 +40,7 @@ if ROOT not in sys.path:
 SLIDERS = dict(smoothing=0.10, glacialErosion=0.50, hydraulicErosion=0.50, thermalErosion=0.10,
                ridgeSharpening=0.50, terrainWarp=0.75)
 SEED = 42
-METRIC = "voronoi_cells_per_sec_terrain_post"
+METRIC = "voronoi_cells_per_sec"
 UNIT = "cells/s"
 
 
@@ -74,9 +79,28 @@ def get_planet(cells: int, seed: int = SEED):
     return mesh, xyz
 
 
-def workload_name(cells, hiters):
-    return (f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), runPostProcessing with default sliders, "
-            f"hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, ridge 3, creep 3")
+def get_inputs(cells: int, seed: int = SEED):
+    """mesh, r_xyz, pre-erosion elevation, r_plate, plateIsOcean — the inputs the hot path receives from the
+    upstream stages (mesh construction, plates, assignElevation), here seeded synthetic stand-ins."""
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plates
+    mesh, xyz = get_planet(cells, SEED)
+    elev0 = synthetic_elevation(xyz, seed, 0.3)
+    r_plate, pio = synthetic_plates(xyz, elev0, seed)
+    return mesh, xyz, elev0, r_plate, pio
+
+
+def workload_name(cells, hiters, workload):
+    post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
+            f"ridge 3, creep 3")
+    clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
+    what = {"post": post, "climate": clim, "full": post + " then " + clim}[workload]
+    return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
+
+
+CLIMATE_REPLY_F32 = (  # the per-cell arrays of the worker's climateDone reply (js/planet-worker.js:635-653)
+    [f"r_wind_{d}_{s}" for s in ("summer", "winter") for d in ("east", "north")]
+    + [f"r_ocean_{k}_{s}" for s in ("summer", "winter") for k in ("current_east", "current_north", "speed", "warmth")]
+    + ["r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter"])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -137,15 +161,23 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline; never the product path)
 # ---------------------------------------------------------------------------------------------------
-def oracle_step_seconds(mesh, xyz, elev0, hiters, steps, warmup):
+def oracle_step_seconds(inputs, hiters, steps, warmup, workload):
     from oracle import binding as oracle
     oracle.build()
+    mesh, xyz, elev0, r_plate, pio = inputs
     nd = oracle.neighbor_dist(mesh, xyz)
+    clim = oracle.Climate(mesh, xyz) if workload != "post" else None
+    e_clim = elev0.copy()
+    if workload == "climate":   # climate runs on the eroded planet: erode once, untimed
+        oracle.run_post_processing(mesh, xyz, e_clim, SLIDERS, nd, SEED, None, hiters)
     times = []
     for i in range(warmup + steps):
-        e = elev0.copy()
+        e = elev0.copy() if workload != "climate" else e_clim
         t = time.perf_counter()
-        oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, None, hiters)
+        if workload != "climate":
+            oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, None, hiters)
+        if workload != "post":
+            clim.run_all(e, pio, r_plate, SEED)
         dt = time.perf_counter() - t
         if i >= warmup:
             times.append(dt)
@@ -166,11 +198,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from planet_heightmap_generation_b200.sphere import synthetic_elevation
-    mesh, xyz = get_planet(args.cells)
-    elev0 = synthetic_elevation(xyz, SEED, 0.3)
-    n = mesh.numRegions
-    times = oracle_step_seconds(mesh, xyz, elev0, args.hiters, args.steps, args.warmup)
+    inputs = get_inputs(args.cells)
+    n = inputs[0].numRegions
+    times = oracle_step_seconds(inputs, args.hiters, args.steps, args.warmup, args.workload)
     total = float(np.sum(times))
     v = n * len(times) / total
     sample = f"full workload, {len(times)} timed passes of {n} cells after {args.warmup} warm-up"
@@ -178,7 +208,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.cells, args.hiters),
+        "config": {"workload": workload_name(args.cells, args.hiters, args.workload),
                    "note": "reference is browser JavaScript (one Web Worker, single thread); no JS runtime in this image, "
                            "so this arm times oracle/ — the C++ -O2 restatement of the same functions — on one host core"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
@@ -191,16 +221,28 @@ def run_reference(args):
 # algorithmic bytes per launch of the kernels that can dominate (DESIGN.md §5 gives the derivation)
 # ---------------------------------------------------------------------------------------------------
 def algorithmic_bytes(name: str, N: int, E: int, land: int):
+    """Compulsory bytes of one launch (every distinct array a pass must touch counted once,
+    neighbour gathers assumed to hit cache).  Keyed by kernel name; None = not tabulated."""
+    csr = 4 * (N + 1) + 4 * E
+    lf = land / max(N, 1)
     table = {
         # order 4 + target 4 + cellDist 4 + flow 4 + elev r/w 8 + isOcean 1 per land cell
         "pb::SolveK": 25 * land,
         # order 4 + pos 4 + target 4 + contrib r/w 8 per land cell
         "pb::AccumulateK": 20 * land,
-        # CSR 4N+4E + elev 4 + isOcean 1 + ndist 4E(land rows) + drainTarget 4 + cellDist 4
-        "pb::ReceiversK": 4 * N + 4 * E + 5 * N + int(4 * E * land / max(N, 1)) + 8 * land,
-        # key 4 + surface 4 + drainTo 4 + visited 1 + elev 4 + CSR row (4 + 4·6) + heap r/w 8 per flooded land cell
-        "pb::FloodSerialK": 53 * land,
-        "pb::SmoothFieldK": 4 * N + 4 * E + 8 * N,
+        # CSR + elev 4 + isOcean 1 + ndist (land rows) + drainTarget 4 + cellDist 4
+        "pb::ReceiversK": csr + 5 * N + int(4 * E * lf) + 8 * land,
+        # per flooded land cell: CSR row (4 + 4·6) + visited 6·1 + elev 6·4 + surface r/w 8 + drainTo 4 + heap entry r/w 16
+        "pb::k_flood_heap": 86 * land,
+        # per filled cell: surface 4 + elev r/w 8 + depth 4 + path reads; tabulated per land cell as in SURVEY §8d (30·L)
+        "pb::k_carve_lift": 30 * land,
+        "pb::SmoothFieldK": csr + 8 * N,
+        "pb::SmoothMaskedK": csr + 9 * N,
+        "pb::DiffuseWarmthK": csr + 12 * N,
+        # offsets + isLand + src + dst for every cell; adj + weight for land rows
+        "pb::ShadowSweepK": 4 * (N + 1) + 9 * N + int(8 * E * lf),
+        # CSR + xyz 12 + wind3d 12 + windE/N 8 + height 4 + src 4 + dst 4 + mask 1
+        "pb::AdvectK": csr + 45 * N,
         "cub::DeviceRadixSort::SortPairs": 4 * 16 * land,
     }
     return table.get(name)
@@ -212,8 +254,8 @@ def algorithmic_bytes(name: str, N: int, E: int, land: int):
 def run_b200(args):
     import torch
     import torch.distributed as dist
+    from planet_heightmap_generation_b200 import climate as cl
     from planet_heightmap_generation_b200.engine import DeviceMesh
-    from planet_heightmap_generation_b200.sphere import synthetic_elevation
     from planet_heightmap_generation_b200.terrain_post import runPostProcessing
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,24 +269,36 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    mesh, xyz = get_planet(args.cells)
+    wl = args.workload
+    do_post, do_clim = wl != "climate", wl != "post"
+    # replicas: every rank processes its own planet (same mesh, different terrain seed)
+    mesh, xyz, elev0_h, r_plate_h, pio = get_inputs(args.cells, SEED + rank)
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
-    # replicas: every rank erodes its own planet (same mesh, different terrain seed)
-    elev0_h = synthetic_elevation(xyz, SEED + rank, 0.3)
     land = int((elev0_h > 0).sum())
     dm = DeviceMesh(mesh, xyz, device=local)
 
     elev0 = torch.from_numpy(elev0_h).to(dev)
+    r_plate = torch.from_numpy(r_plate_h).to(dev)
     elev = torch.empty_like(elev0)
     delta = torch.empty_like(elev0)
     ocean = torch.empty(N, dtype=torch.uint8, device=dev)
+    koppen = torch.empty(N, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_device():
-        flush.zero_()
+    def post_device():
         elev.copy_(elev0)    # handleReapply clones W.prePostElev before post-processing (planet-worker.js:353)
         runPostProcessing(dm, None, elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
                           out_erosionDelta=delta, out_isOcean=ocean, timing=False)
+
+    if not do_post:          # climate-only: the eroded planet is the (untimed) input
+        post_device()
+
+    def step_device():
+        flush.zero_()
+        if do_post:
+            post_device()
+        if do_clim:
+            cl.computeClimate(dm, elev, pio, r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
 
     def barrier():
         torch.cuda.synchronize()
@@ -252,16 +306,29 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 1, 0)):
         step_device()
+    # last warm-up step is fully profiled: it names the dominant kernel (largest total device time)
+    dm.profile_start(None)
+    step_device()
+    rows = sorted(dm.profile_stop(), key=lambda p: -p["ms"])
     barrier()
+    dominant = args.dominant or (rows[0]["name"] if rows else "")
+    sweep_kernel = "pb::SmoothFieldK" if do_clim else "pb::SolveK"
+    breakdown = None
+    if rank == 0:
+        tot = sum(p["ms"] for p in rows)
+        breakdown = [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 3)} for p in rows[:14]]
+        log(f"[bench] per-kernel device time of one warm-up step (events around every launch, sum {tot:.1f} ms):")
+        for p in rows[:30]:
+            log(f"   {p['ms']:10.3f} ms  {p['launches']:6d}x  {p['name']}")
 
-    dominant = args.dominant
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = dm.launch_count()
-    dm.profile_start(dominant)
+    # events around the launches of the dominant kernel and of the most-launched sweep kernel only
+    dm.profile_start(dominant if dominant == sweep_kernel else "|".join([dominant, sweep_kernel]))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -284,16 +351,31 @@ def run_b200(args):
 
     # ---- end to end through the host-pointer C ABI ------------------------------------------------
     h_elev0 = torch.from_numpy(elev0_h).pin_memory()
+    h_plate = torch.from_numpy(r_plate_h).pin_memory()
     h_elev = torch.empty(N, dtype=torch.float32).pin_memory()
     h_delta = torch.empty(N, dtype=torch.float32).pin_memory()
     h_ocean = torch.empty(N, dtype=torch.uint8).pin_memory()
-    np_elev, np_delta, np_ocean = h_elev.numpy(), h_delta.numpy(), h_ocean.numpy()
+    h_koppen = torch.empty(N, dtype=torch.uint8).pin_memory()
+    np_elev, np_delta, np_ocean, np_koppen, np_plate = (h_elev.numpy(), h_delta.numpy(), h_ocean.numpy(),
+                                                       h_koppen.numpy(), h_plate.numpy())
+    if not do_post:
+        h_elev.copy_(elev.cpu())
+    h2d = (4 * N if do_post else 0) + (8 * N if do_clim else 0)
+    d2h = (9 * N if do_post else 0) + ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
+    reply = {}
 
     def step_host():
         flush.zero_()
-        h_elev.copy_(h_elev0)
-        runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
-                          out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
+        if do_post:
+            h_elev.copy_(h_elev0)
+            runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
+                              out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
+        if do_clim:
+            w, o, p, t, _ = cl.computeClimate(dm, np_elev, pio, np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
+            for res, keys in ((w, CLIMATE_REPLY_F32[:4] + ["itczLons", "itczLatsSummer", "itczLatsWinter"]),
+                              (o, CLIMATE_REPLY_F32[4:12]), (p, CLIMATE_REPLY_F32[12:14]), (t, CLIMATE_REPLY_F32[14:])):
+                for k in keys:
+                    reply[k] = res[k]     # device → host copy of every array of the climateDone message
 
     step_host()
     barrier()
@@ -307,44 +389,39 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = N * world * args.steps / e2e_s
-    same = bool((h_elev == elev.cpu()).all().item())   # host-pointer and device-pointer passes agree bit for bit
+    # host-pointer and device-pointer passes agree bit for bit
+    same = bool((h_elev == elev.cpu()).all().item()) and (not do_clim or bool((h_koppen == koppen.cpu()).all().item()))
 
-    # ---- roofline of the dominant kernel (events recorded inside the timed region) ---------------------
+    # ---- roofline (events recorded inside the timed region) ---------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    roofline = None
-    dom = [p for p in prof if p["name"] == dominant or dominant in p["name"]]
-    if dom:
-        d = max(dom, key=lambda p: p["ms"])
-        ab = algorithmic_bytes(d["name"], N, E, land)
-        if ab:
-            avg_ms = d["ms"] / d["launches"]
-            achieved = ab / (avg_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": d["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": ab,
-                        "avg_launch_ms": avg_ms, "launches_timed": d["launches"],
-                        "share_of_step": d["ms"] / ms_total, "peak_source": peak_src}
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if "hbm_gbs" in peaks else "fallback 6650 GB/s, of fallback"
 
-    # ---- one more fully profiled step: per-kernel breakdown (not part of any reported number) ---------
-    breakdown = None
-    if rank == 0 and not args.no_breakdown:
-        dm.profile_start(None)
-        step_device()
-        rows = sorted(dm.profile_stop(), key=lambda p: -p["ms"])
-        tot = sum(p["ms"] for p in rows)
-        breakdown = [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 3)} for p in rows[:12]]
-        log(f"[bench] per-kernel device time of one step (events around every launch, sum {tot:.1f} ms):")
-        for p in rows[:25]:
-            log(f"   {p['ms']:10.3f} ms  {p['launches']:6d}x  {p['name']}")
+    def roof(kernel):
+        dom = [p for p in prof if p["name"] == kernel]
+        if not dom:
+            return None
+        d = dom[0]
+        ab = algorithmic_bytes(d["name"], N, E, land)
+        avg_ms = d["ms"] / d["launches"]
+        out = {"bound": "hbm", "kernel": d["name"], "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+               "traffic": None, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms,
+               "launches_timed": d["launches"], "share_of_step": d["ms"] / ms_total, "peak_source": peak_src}
+        if ab:
+            out["achieved"] = ab / (avg_ms * 1e-3) / 1e9
+            out["frac"] = out["achieved"] / peak
+        return out
+
+    roofline = roof(dominant)
+    roofline_sweep = roof(sweep_kernel) if sweep_kernel != dominant else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        times = oracle_step_seconds(mesh, xyz, elev0_h, args.hiters, 1, 0)
+        times = oracle_step_seconds((mesh, xyz, elev0_h, r_plate_h, pio), args.hiters, 1, 0, wl)
         cpu_baseline = {"value": N / times[0], "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread",
                         "cpu": cpu_model(), "host_cores": os.cpu_count()}
@@ -354,15 +431,17 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.cells, args.hiters), "cells_per_gpu": N,
+            "config": {"workload": workload_name(args.cells, args.hiters, wl), "cells_per_gpu": N,
                        "multi_gpu": "replicas (one planet per GPU, no data-path collective)" if world > 1 else "single",
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
-                       "land_cells": land},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * N * world,
-                    "d2h_bytes_per_step": 9 * N * world, "ms_per_step": 1000 * e2e_s / args.steps,
+                       "land_cells": land,
+                       "inputs": "mesh, pre-erosion elevation and plates are seeded synthetic stand-ins for the upstream "
+                                 "stages (mesh construction, plates, assignElevation), resident before the timed region"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernel_breakdown": breakdown, "library": dm.lib.version,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
+            "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "library": dm.lib.version,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -374,11 +453,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate"])
     ap.add_argument("--cells", type=int, default=1_000_000)
     ap.add_argument("--hiters", type=int, default=50)
-    ap.add_argument("--dominant", default="pb::SolveK", help="kernel whose launches are event-timed for the roofline")
+    ap.add_argument("--dominant", default="", help="kernel whose launches are event-timed for the roofline "
+                                                   "(default: the kernel with the largest device time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-breakdown", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: fewer than 3 warm-up steps requested")

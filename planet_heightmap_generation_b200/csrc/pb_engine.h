@@ -212,40 +212,25 @@ struct Mesh {
     DevBuf<int> liftUp, liftDepthA, liftDepthB;
     int floodSmemMax = -1;
     int lastMaxHeap = 0;
-    // `reinit` re-runs the per-cell initialisation (needed when the shared-memory-only variant overflowed)
-    template <class Reinit>
-    void flood_heap_cuda(const float* elev, Reinit reinit) {
+    void flood_heap_cuda(const float* elev) {
         const Exec& x = ex();
         if (floodSmemMax < 0) {
             int dev = 0, v = 0;
             PB_CUDA_CHECK(cudaGetDevice(&dev));
             PB_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
             floodSmemMax = v - 2048;    // static shared + reserve
-            PB_CUDA_CHECK(cudaFuncSetAttribute(k_flood_heap<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, floodSmemMax));
-            PB_CUDA_CHECK(cudaFuncSetAttribute(k_flood_heap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, floodSmemMax));
+            PB_CUDA_CHECK(cudaFuncSetAttribute(k_flood_heap, cudaFuncAttributeMaxDynamicSharedMemorySize, floodSmemMax));
         }
         const int cap = ((int)(floodSmemMax / sizeof(HeapEntry)) - 4) & ~1;
         FloodHeapArgs a{csr(), elev, surface.p, drainTo.p, visited.p, seeds.p, counters.p + 0,
                         heapSpill.ensure(N), cap, counters.p + 12};
-        dev_memset(counters.p + 12, 0, 2 * sizeof(int), x.stream);
-        {
-            launch_stats().launches++;
-            ProfScope ps(x.prof, "pb::k_flood_heap", x.stream);
-            k_flood_heap<false><<<1, PB_FLOOD_THREADS, floodSmemMax, x.stream>>>(a);
-            PB_CUDA_CHECK(cudaGetLastError());
-        }
-        int st[2];
-        dev_copy(st, counters.p + 12, sizeof st, 1, x.stream);
-        stream_sync(x.stream);
-        lastMaxHeap = st[0];
-        if (getenv("PB_DEBUG")) fprintf(stderr, "[pb] flood: max heap %d of %d shared entries%s\n", st[0], cap, st[1] ? " (overflow → spill variant)" : "");
-        if (st[1]) {   // the frontier outgrew shared memory: redo with the global-memory tail
-            reinit();
-            dev_memset(counters.p + 12, 0, 2 * sizeof(int), x.stream);
-            launch_stats().launches++;
-            ProfScope ps(x.prof, "pb::k_flood_heap(spill)", x.stream);
-            k_flood_heap<true><<<1, PB_FLOOD_THREADS, floodSmemMax, x.stream>>>(a);
-            PB_CUDA_CHECK(cudaGetLastError());
+        launch_stats().launches++;
+        ProfScope ps(x.prof, "pb::k_flood_heap", x.stream);
+        k_flood_heap<<<1, PB_FLOOD_THREADS, floodSmemMax, x.stream>>>(a);
+        PB_CUDA_CHECK(cudaGetLastError());
+        if (getenv("PB_DEBUG")) {
+            lastMaxHeap = read_int(counters.p + 12);
+            fprintf(stderr, "[pb] flood: max heap %d (%d entries fit in shared memory)\n", lastMaxHeap, cap);
         }
     }
     // pass 2: binary lifting over the flood forest, one CTA per flood tree (pb_flood.h)
@@ -294,9 +279,7 @@ struct Mesh {
         seeds.ensure(N); heap.ensure(N);
         prims.compact_flagged(x, seedFlag.p, N, seeds.p, counters.p + 0);
 #if PB_CUDA
-        flood_heap_cuda(elev, [&] {
-            x.for_each(N, FloodInitK{g, elev, isOcean, parent.p, best.p, surface.p, key.p, drainTo.p, visited.p, seedFlag.p, oo});
-        });
+        flood_heap_cuda(elev);
 #else
         x.single(FloodSerialK{g, elev, surface.p, key.p, drainTo.p, visited.p, seeds.p, counters.p + 0, heap.p});
 #endif

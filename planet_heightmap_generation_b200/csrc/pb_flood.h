@@ -278,65 +278,66 @@ namespace pb {
 
 // ---- (1) heap flood: one CTA --------------------------------------------------------------------
 // The reference's binary MinHeap has to be replayed operation by operation (ties between equal f32
-// keys are resolved by heap layout), so pass 1 is one serial chain of ~|land| pops.
-// What can be done is to make every link of the chain cheap:
+// keys are resolved by heap layout), so pass 1 is one serial chain of ~|land| pops and
+// a single warp issues dependent instructions at only ~0.23 per cycle (ncu: 42 % fixed-latency
+// dependency stalls, profiles/r01_flood_heap_ncu.md).  What can be done is to make every link cheap:
 //   * the heap lives in shared memory as (key, cell) pairs — keys never change once pushed, so the
-//     inline copy is exact and a sift step is one 16-byte LDS (both children) instead of four
-//     dependent L2 round trips; entries beyond the shared-memory capacity spill to global memory;
-//   * warp 0 replays the heap; its 32 lanes expand the popped cell's neighbours in parallel and the
-//     row / surface loads of the popped cell are issued before the sift-down so they overlap it;
+//     inline copy is exact and a sift step is one 16-byte LDS (both children) plus ~14 instructions
+//     instead of four dependent L2 round trips; nodes beyond the shared capacity spill to global memory;
+//   * the 32 lanes expand the popped cell's neighbours in parallel, and the loads of the popped cell
+//     are issued before the sift-down so they overlap it;
 //   * the other warps keep the CSR rows and neighbour elevations of the current heap top resident
-//     in L1 (plain read-only prefetching; they never write).
+//     in L1 (read-only prefetching of immutable arrays; the visited flags are read through L2).
+// (A warp-cooperative sift that resolves four levels per round was measured 2.2× slower than this
+// scalar form: ballots and shuffles cost more dependent instructions than they save.)
 struct HeapEntry { uint32_t k; int c; };   // k = __float_as_uint(key); keys compare as floats
 
 struct FloodHeapArgs {
     Csr g; const float* elev; float* surface; int* drainTo; uint8_t* visited;
     const int* seeds; const int* nSeeds; HeapEntry* spill; int cap;
-    int* status;   // [0] max heap size reached, [1] set to 1 when the no-spill variant ran out of shared memory
+    int* status;   // [0] max heap size reached
 };
 
-#define PB_FLOOD_THREADS 128
+#define PB_FLOOD_THREADS 64
 
-// Heap storage: node j lives in slot j+1 of the shared array, so the two children of a node share
-// one aligned 16-byte word.  SPILL adds a global-memory tail for nodes >= cap.
-template <bool SPILL>
+// node j lives in shared slot j+1 for j < cap (so the two children of a node share one aligned
+// 16-byte word), else in the global tail
 struct HeapStore {
     HeapEntry* sh; HeapEntry* spill; int cap;
-    __device__ __forceinline__ HeapEntry ld(int i) const {
-        if (!SPILL || i < cap) return sh[i + 1];
-        const uint2 v = __ldcg((const uint2*)(spill + (i - cap)));
+    __device__ __forceinline__ HeapEntry ld(int j) const {
+        if (j < cap) return sh[j + 1];
+        const uint2 v = __ldcg((const uint2*)(spill + (j - cap)));
         HeapEntry e; e.k = v.x; e.c = (int)v.y;
         return e;
     }
-    __device__ __forceinline__ void st(int i, HeapEntry e) const {
-        if (!SPILL || i < cap) sh[i + 1] = e;
-        else __stcg((uint2*)(spill + (i - cap)), make_uint2(e.k, (uint32_t)e.c));
+    __device__ __forceinline__ void st(int j, HeapEntry e) const {
+        if (j < cap) sh[j + 1] = e;
+        else __stcg((uint2*)(spill + (j - cap)), make_uint2(e.k, (uint32_t)e.c));
     }
-    // children l and l+1 of a node; the right one may be beyond n (caller checks)
-    __device__ __forceinline__ void ld2(int l, HeapEntry& le, HeapEntry& re) const {
-        if (!SPILL || l + 1 < cap) {
+    __device__ __forceinline__ void ld2(int l, HeapEntry& le, HeapEntry& re) const {   // children l, l+1
+        if (l + 1 < cap) {
             const uint4 v = *(const uint4*)(sh + l + 1);
             le.k = v.x; le.c = (int)v.y; re.k = v.z; re.c = (int)v.w;
         } else { le = ld(l); re = ld(l + 1); }
     }
 };
 
-template <bool SPILL>
 __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeapEntry* sh = (HeapEntry*)smem_raw;                                  // [cap + 2]
     __shared__ volatile int done;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.g.N;
+    const unsigned FULL = 0xffffffffu;
     if (tid == 0) done = 0;
     for (int w = tid; w < 64; w += blockDim.x) sh[w].c = 0;                  // helpers may peek before the first push
     __syncthreads();
 
     if (warp != 0) {
-        // ---- prefetch helpers: keep the rows of the heap's top entries hot in L1 -------------------
+        // ---- prefetch helper: keep the rows of the heap's top entries hot in L1 -------------------
         const int nHelpers = (blockDim.x >> 5) - 1;
         while (!done) {
-            for (int idx = warp - 1; idx < 15; idx += nHelpers) {
+            for (int idx = warp - 1; idx < 7; idx += nHelpers) {
                 int c = ((volatile HeapEntry*)sh)[idx + 1].c;
                 if (c < 0 || c >= N) continue;
                 const int b = __ldg(a.g.off + c), e = __ldg(a.g.off + c + 1);
@@ -345,17 +346,15 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                     if (nb >= 0 && nb < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
                 }
             }
-            __nanosleep(100);
+            __nanosleep(200);
         }
         return;
     }
 
     // ---- warp 0: the heap engine.  All 32 lanes run the heap operations redundantly (same addresses,
-    // same values), which keeps the warp converged; a single warp issues dependent instructions at
-    // roughly one per 4-6 cycles, so the loops below are written for the fewest instructions per level.
-    const HeapStore<SPILL> H{sh, a.spill, a.cap};
+    // same values), which keeps the warp converged.
+    const HeapStore H{sh, a.spill, a.cap};
     int n = 0, maxN = 0;
-    bool overflow = false;
     auto push = [&](uint32_t kbits, int cell) {
         int i = n++;
         const float kc = __uint_as_float(kbits);
@@ -370,8 +369,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         H.st(i, me);
     };
     const int ns = *a.nSeeds;
-    if (!SPILL && ns + 64 > a.cap) overflow = true;
-    for (int s = 0; s < ns && !overflow; s++) {
+    for (int s = 0; s < ns; s++) {
         const int c = a.seeds[s];
         const float k = (float)((double)__ldg(a.elev + c) + cell_noise(c));
         push(__float_as_uint(k), c);
@@ -381,7 +379,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     int b = 0, e = 0;
     float surfRf = 0.f;
     if (r >= 0) { b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r); }
-    while (n > 0 && !overflow) {
+    while (n > 0) {
         if (n > maxN) maxN = n;
         // neighbour ids of the popped cell: in flight while the sift-down runs
         int nb = -1;
@@ -405,11 +403,10 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
             H.st(i, last);
         }
         __syncwarp();
-        // expand r: lane j owns neighbour j
+        // expand r: lane j owns neighbour j; visited flag and elevation are fetched together
         const double surfR = (double)surfRf;
         uint32_t kbits = 0; bool fresh = false;
         if (nb >= 0) {
-            // visited flag and elevation are fetched together (one L2 round trip on the critical path)
             const bool v = __ldcg(a.visited + nb) != 0;
             const float el = __ldg(a.elev + nb);
             const double noise = cell_noise(nb);
@@ -422,13 +419,12 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                 __stcg(a.visited + nb, (uint8_t)1);
             }
         }
-        unsigned m = __ballot_sync(0xffffffffu, fresh);
-        if (!SPILL && n + __popc(m) + 2 > a.cap) { overflow = true; break; }
+        unsigned m = __ballot_sync(FULL, fresh);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
-            const uint32_t kk = __shfl_sync(0xffffffffu, kbits, src);
-            const int cc = __shfl_sync(0xffffffffu, nb, src);
+            const uint32_t kk = __shfl_sync(FULL, kbits, src);
+            const int cc = __shfl_sync(FULL, nb, src);
             push(kk, cc);
         }
         __syncwarp();
@@ -438,7 +434,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
             b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r);
         }
     }
-    if (lane == 0) { done = 1; a.status[0] = maxN; if (overflow) a.status[1] = 1; }
+    if (lane == 0) { done = 1; a.status[0] = maxN; }
 }
 
 // ---- (2) carve: binary lifting over the flood forest, one CTA per flood tree ---------------------------

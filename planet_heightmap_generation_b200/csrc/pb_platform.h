@@ -190,7 +190,20 @@ struct Profiler {
         free(dm);
         return readable[name] = out;
     }
-    bool wants(const char* name) { return on && (filter.empty() || pretty(name).find(filter) != std::string::npos); }
+    // filter: empty = everything, else '|'-separated substrings
+    bool wants(const char* name) {
+        if (!on) return false;
+        if (filter.empty()) return true;
+        const std::string& p = pretty(name);
+        size_t b = 0;
+        while (b <= filter.size()) {
+            size_t e = filter.find('|', b);
+            if (e == std::string::npos) e = filter.size();
+            if (e > b && p.find(filter.substr(b, e - b)) != std::string::npos) return true;
+            b = e + 1;
+        }
+        return false;
+    }
     void start(const char* f) {
         collect(nullptr);
         filter = f ? f : "";
