@@ -98,6 +98,7 @@ struct Mesh {
     DevBuf<float> surface, key, e0;
     DevBuf<uint8_t> visited, seedFlag, rootActive, openOcean;
     DevBuf<unsigned long long> best;
+    DevBuf<double> cellNoiseBuf;
     // erosion
     DevBuf<int> order, pos, drainTarget, cnt, k0, k1, k2, iceTarget, kSelf;
     DevBuf<float> cellDist, flow, contrib, glacIdx, iceFlow;
@@ -222,7 +223,7 @@ struct Mesh {
             PB_CUDA_CHECK(cudaFuncSetAttribute(k_flood_heap, cudaFuncAttributeMaxDynamicSharedMemorySize, floodSmemMax));
         }
         const int cap = ((int)(floodSmemMax / sizeof(HeapEntry)) - 4) & ~1;
-        FloodHeapArgs a{csr(), elev, surface.p, drainTo.p, visited.p, seeds.p, counters.p + 0,
+        FloodHeapArgs a{csr(), elev, surface.p, drainTo.p, visited.p, key.p, cellNoiseBuf.p, seeds.p, counters.p + 0,
                         heapSpill.ensure(N), cap, counters.p + 12};
         launch_stats().launches++;
         ProfScope ps(x.prof, "pb::k_flood_heap", x.stream);
@@ -274,7 +275,7 @@ struct Mesh {
 
         surface.ensure(N); key.ensure(N); drainTo.ensure(N); visited.ensure(N); seedFlag.ensure(N);
         uint8_t* oo = (taps && taps->openOcean) ? taps->openOcean : nullptr;
-        x.for_each(N, FloodInitK{g, elev, isOcean, parent.p, best.p, surface.p, key.p, drainTo.p, visited.p, seedFlag.p, oo});
+        x.for_each(N, FloodInitK{g, elev, isOcean, parent.p, best.p, surface.p, key.p, drainTo.p, visited.p, seedFlag.p, oo, cellNoiseBuf.ensure(N)});
         counters.ensure(16);
         seeds.ensure(N); heap.ensure(N);
         prims.compact_flagged(x, seedFlag.p, N, seeds.p, counters.p + 0);

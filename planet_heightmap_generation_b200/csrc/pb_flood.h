@@ -81,11 +81,13 @@ PB_DEV bool is_open_ocean(int r, const uint8_t* isOcean, const int* parent, cons
 // ---- (1) keys, seeds, heap flood ----------------------------------------------------------------
 struct FloodInitK {
     Csr g; const float* elev; const uint8_t* isOcean; const int* parent; const unsigned long long* best;
-    float* surface; float* key; int* drainTo; uint8_t* visited; uint8_t* seedFlag; uint8_t* openOcean;
+    float* surface; float* key; int* drainTo; uint8_t* visited; uint8_t* seedFlag; uint8_t* openOcean; double* noise;
     PB_DEV void operator()(int r) const {
         const float e = elev[r];
         surface[r] = e;
-        key[r] = (float)((double)e + cell_noise(r));
+        const double cn = cell_noise(r);
+        if (noise) noise[r] = cn;
+        key[r] = (float)((double)e + cn);
         int dt = -1; uint8_t vis = 0, seed = 0;
         if (isOcean[r]) {
             vis = 1;
@@ -294,11 +296,12 @@ struct HeapEntry { uint32_t k; int c; };   // k = __float_as_uint(key); keys com
 
 struct FloodHeapArgs {
     Csr g; const float* elev; float* surface; int* drainTo; uint8_t* visited;
+    const float* key0; const double* noise;   // initial keys f32(elev + cellNoise) and cellNoise per cell (FloodInitK)
     const int* seeds; const int* nSeeds; HeapEntry* spill; int cap;
     int* status;   // [0] max heap size reached
 };
 
-#define PB_FLOOD_THREADS 64
+#define PB_FLOOD_THREADS 128
 
 // node j lives in shared slot j+1 for j < cap (so the two children of a node share one aligned
 // 16-byte word), else in the global tail
@@ -313,12 +316,6 @@ struct HeapStore {
     __device__ __forceinline__ void st(int j, HeapEntry e) const {
         if (j < cap) sh[j + 1] = e;
         else __stcg((uint2*)(spill + (j - cap)), make_uint2(e.k, (uint32_t)e.c));
-    }
-    __device__ __forceinline__ void ld2(int l, HeapEntry& le, HeapEntry& re) const {   // children l, l+1
-        if (l + 1 < cap) {
-            const uint4 v = *(const uint4*)(sh + l + 1);
-            le.k = v.x; le.c = (int)v.y; re.k = v.z; re.c = (int)v.w;
-        } else { le = ld(l); re = ld(l + 1); }
     }
 };
 
@@ -337,7 +334,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         // ---- prefetch helper: keep the rows of the heap's top entries hot in L1 -------------------
         const int nHelpers = (blockDim.x >> 5) - 1;
         while (!done) {
-            for (int idx = warp - 1; idx < 7; idx += nHelpers) {
+            for (int idx = warp - 1; idx < 15; idx += nHelpers) {
                 int c = ((volatile HeapEntry*)sh)[idx + 1].c;
                 if (c < 0 || c >= N) continue;
                 const int b = __ldg(a.g.off + c), e = __ldg(a.g.off + c + 1);
@@ -346,7 +343,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                     if (nb >= 0 && nb < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
                 }
             }
-            __nanosleep(200);
+            __nanosleep(100);
         }
         return;
     }
@@ -355,27 +352,38 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     // same values), which keeps the warp converged.
     const HeapStore H{sh, a.spill, a.cap};
     int n = 0, maxN = 0;
+    // The shared-memory paths are kept free of any global-tail code: mixing both in one loop costs the
+    // fast path a factor ~2.8 (measured), although the tail is hardly ever touched.
+    const int cap = a.cap;
     auto push = [&](uint32_t kbits, int cell) {
         int i = n++;
         const float kc = __uint_as_float(kbits);
-        while (i > 0) {
+        bool placed = false;
+        while (i >= cap) {                                       // slow: node in the global tail
             const int p = (i - 1) >> 1;
             const HeapEntry pe = H.ld(p);
-            if (kc >= __uint_as_float(pe.k)) break;          // MinHeap.push stops on >=   (:22)
+            if (kc >= __uint_as_float(pe.k)) { placed = true; break; }
             H.st(i, pe);
             i = p;
         }
+        if (!placed)
+            while (i > 0) {                                      // fast: shared memory only
+                const int p = (i - 1) >> 1;
+                const HeapEntry pe = sh[p + 1];
+                if (kc >= __uint_as_float(pe.k)) break;          // MinHeap.push stops on >=   (:22)
+                sh[i + 1] = pe;
+                i = p;
+            }
         HeapEntry me; me.k = kbits; me.c = cell;
-        H.st(i, me);
+        if (i < cap) sh[i + 1] = me; else H.st(i, me);
     };
     const int ns = *a.nSeeds;
     for (int s = 0; s < ns; s++) {
         const int c = a.seeds[s];
-        const float k = (float)((double)__ldg(a.elev + c) + cell_noise(c));
-        push(__float_as_uint(k), c);
+        push(__float_as_uint(__ldg(a.key0 + c)), c);
     }
     __syncwarp();
-    int r = n > 0 ? H.ld(0).c : -1;
+    int r = n > 0 ? sh[1].c : -1;
     int b = 0, e = 0;
     float surfRf = 0.f;
     if (r >= 0) { b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r); }
@@ -385,22 +393,38 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         int nb = -1;
         if (b + lane < e) nb = __ldg(a.g.adj + b + lane);
         // pop: MinHeap.pop (:27-46) — last → root, sift down along the min-child path (left child on ties)
-        const HeapEntry last = H.ld(--n);
+        --n;
+        const HeapEntry last = n < cap ? sh[n + 1] : H.ld(n);
         if (n > 0) {
             const float kl = __uint_as_float(last.k);
             int i = 0;
-            for (;;) {
+            bool placed = false;
+            for (;;) {                                           // fast: both children in shared memory
                 const int l = 2 * i + 1;
-                if (l >= n) break;
-                HeapEntry le, re;
-                H.ld2(l, le, re);
-                const bool right = (l + 1 < n) && (__uint_as_float(re.k) < __uint_as_float(le.k));
-                HeapEntry m; m.k = right ? re.k : le.k; m.c = right ? re.c : le.c;
-                if (!(__uint_as_float(m.k) < kl)) break;
-                H.st(i, m);
+                if (l >= n) { placed = true; break; }
+                if (l + 1 >= cap) break;
+                const uint4 v = *(const uint4*)(sh + l + 1);
+                const bool right = (l + 1 < n) && (__uint_as_float(v.z) < __uint_as_float(v.x));
+                const uint32_t mk = right ? v.z : v.x;
+                if (!(__uint_as_float(mk) < kl)) { placed = true; break; }
+                HeapEntry m; m.k = mk; m.c = (int)(right ? v.w : v.y);
+                sh[i + 1] = m;
                 i = l + (right ? 1 : 0);
             }
-            H.st(i, last);
+            if (!placed)
+                for (;;) {                                       // slow: children in the global tail
+                    const int l = 2 * i + 1;
+                    if (l >= n) break;
+                    const HeapEntry le = H.ld(l);
+                    HeapEntry re = le;
+                    if (l + 1 < n) re = H.ld(l + 1);
+                    const bool right = (l + 1 < n) && (__uint_as_float(re.k) < __uint_as_float(le.k));
+                    const HeapEntry m = right ? re : le;
+                    if (!(__uint_as_float(m.k) < kl)) break;
+                    H.st(i, m);
+                    i = l + (right ? 1 : 0);
+                }
+            if (i < cap) sh[i + 1] = last; else H.st(i, last);
         }
         __syncwarp();
         // expand r: lane j owns neighbour j; visited flag and elevation are fetched together
@@ -409,12 +433,17 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         if (nb >= 0) {
             const bool v = __ldcg(a.visited + nb) != 0;
             const float el = __ldg(a.elev + nb);
-            const double noise = cell_noise(nb);
+            const float k0 = __ldg(a.key0 + nb);
+            const double noise = __ldg(a.noise + nb);
             if (!v) {
                 fresh = true;
-                float s = el;
-                if ((double)el < surfR + PB_FLOOD_EPS) { s = (float)(surfR + PB_FLOOD_EPS); __stcg(a.surface + nb, s); }
-                kbits = __float_as_uint((float)((double)s + noise));
+                float kf = k0;
+                if ((double)el < surfR + PB_FLOOD_EPS) {
+                    const float s = (float)(surfR + PB_FLOOD_EPS);
+                    __stcg(a.surface + nb, s);
+                    kf = (float)((double)s + noise);
+                }
+                kbits = __float_as_uint(kf);
                 __stcg(a.drainTo + nb, r);
                 __stcg(a.visited + nb, (uint8_t)1);
             }
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         __syncwarp();
         // next pop is the root now; start its row / surface loads right away
         if (n > 0) {
-            r = H.ld(0).c;
+            r = sh[1].c;
             b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r);
         }
     }
