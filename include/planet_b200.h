@@ -55,6 +55,10 @@ const char* pb_version(void);
 pb_status pb_set_stream(pb_context* ctx, void* cuda_stream);
 pb_status pb_set_pointer_mode(pb_context* ctx, int mode);
 pb_status pb_synchronize(pb_context* ctx);
+/* Engine options (name, value).  "flood": "device" (default — the heap flood of priorityFloodCarve runs as a
+ * one-CTA CUDA kernel) or "host" (that one serial pass runs on a host core; everything else stays on the GPU;
+ * results are identical). */
+pb_status pb_set_option(pb_context* ctx, const char* name, const char* value);
 /* kernels launched by this library on any context since process start (bench: gpu_launches) */
 int64_t pb_launch_count(void);
 

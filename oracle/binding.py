@@ -37,6 +37,9 @@ def lib():
         _LIB.orc_percentile.restype = C.c_double
         _LIB.orc_climate_create.restype = C.c_void_p
         _LIB.orc_climate_get.restype = C.c_int64
+        _LIB.orc_elev_create.restype = C.c_void_p
+        _LIB.orc_elev_get.restype = C.c_int64
+        _LIB.orc_pair_intensity.restype = C.c_double
     return _LIB
 
 
@@ -243,3 +246,63 @@ def compute_gradients(mesh, xyz, field, frames6):
 
 def smooth_masked(mesh, field, mask, passes):
     lib().orc_smooth_masked(*_mesh_args(mesh), _p(field, C.c_float), _p(mask, C.c_uint8), C.c_int(passes))
+
+
+# ---- elevation (oracle/elevation.cpp) --------------------------------------------------------------------
+def plate_table_arrays(table):
+    """table: dict pid -> dict(isOcean=bool, pole=(x,y,z), omega=float, density=float), insertion-ordered."""
+    ids = np.ascontiguousarray(list(table.keys()), np.int32)
+    oc = np.ascontiguousarray([1 if table[k]["isOcean"] else 0 for k in table], np.uint8)
+    pole = np.ascontiguousarray([table[k]["pole"] for k in table], np.float64).reshape(-1)
+    omega = np.ascontiguousarray([table[k]["omega"] for k in table], np.float64)
+    dens = np.ascontiguousarray([table[k]["density"] for k in table], np.float64)
+    return ids, oc, pole, omega, dens
+
+
+class Elevation:
+    """assignElevation (js/elevation.js:216-1391); every intermediate kept under a readable name."""
+
+    def __init__(self, mesh, xyz):
+        self.mesh = mesh
+        self.xyz = np.ascontiguousarray(xyz, np.float32)
+        self._off = np.ascontiguousarray(mesh.adjOffset, np.int32)
+        self._adj = np.ascontiguousarray(mesh.adjList, np.int32)
+        self._h = C.c_void_p(lib().orc_elev_create(C.c_int(mesh.numRegions), _p(self._off, C.c_int32),
+                                                   _p(self._adj, C.c_int32), _p(self.xyz, C.c_float)))
+
+    def __del__(self):
+        try:
+            lib().orc_elev_destroy(self._h)
+        except Exception:
+            pass
+
+    def assign(self, r_plate, plates, plate_seeds, noise_seed, noise_mag, seed, spread, r_super=None, super_plates=None):
+        r_plate = np.ascontiguousarray(r_plate, np.int32)
+        ids, oc, pole, om, de = plate_table_arrays(plates)
+        seeds = np.ascontiguousarray(list(plate_seeds), np.int32)
+        if super_plates:
+            r_super = np.ascontiguousarray(r_super, np.int32)
+            sids, soc, spole, som, sde = plate_table_arrays(super_plates)
+            lib().orc_elev_assign(self._h, _p(r_plate, C.c_int32), C.c_int(ids.size), _p(ids, C.c_int32), _p(oc, C.c_uint8),
+                                  _p(pole, C.c_double), _p(om, C.c_double), _p(de, C.c_double), _p(seeds, C.c_int32),
+                                  C.c_int(seeds.size), C.c_double(noise_seed), C.c_double(noise_mag), C.c_double(seed),
+                                  C.c_double(spread), _p(r_super, C.c_int32), C.c_int(sids.size), _p(sids, C.c_int32),
+                                  _p(soc, C.c_uint8), _p(spole, C.c_double), _p(som, C.c_double), _p(sde, C.c_double))
+        else:
+            lib().orc_elev_assign(self._h, _p(r_plate, C.c_int32), C.c_int(ids.size), _p(ids, C.c_int32), _p(oc, C.c_uint8),
+                                  _p(pole, C.c_double), _p(om, C.c_double), _p(de, C.c_double), _p(seeds, C.c_int32),
+                                  C.c_int(seeds.size), C.c_double(noise_seed), C.c_double(noise_mag), C.c_double(seed),
+                                  C.c_double(spread), None, C.c_int(0), None, None, None, None, None)
+
+    def get(self, name, dtype=np.float32):
+        kind = _KIND[np.dtype(dtype)]
+        n = lib().orc_elev_get(self._h, name.encode(), C.c_int(kind), None, C.c_int64(0))
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype)
+        lib().orc_elev_get(self._h, name.encode(), C.c_int(kind), out.ctypes.data_as(C.c_void_p), C.c_int64(n))
+        return out
+
+
+def pair_intensity(a, b):
+    return lib().orc_pair_intensity(C.c_int(a), C.c_int(b))

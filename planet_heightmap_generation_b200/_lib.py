@@ -35,6 +35,7 @@ SYMBOLS = {
     "pb_set_stream": (C.c_int, [_vp, _vp]),
     "pb_set_pointer_mode": (C.c_int, [_vp, C.c_int]),
     "pb_synchronize": (C.c_int, [_vp]),
+    "pb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "pb_launch_count": (_i64, []),
     "pb_profile_start": (C.c_int, [_vp, C.c_char_p]),
     "pb_profile_stop": (C.c_int, [_vp, C.c_char_p, _i64]),

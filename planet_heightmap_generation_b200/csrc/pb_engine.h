@@ -18,6 +18,7 @@ inline double js_round(double x) { return floor(x + 0.5); }   // Math.round
 struct Context {
     int device = 0;
     int pointerMode = PB_POINTER_HOST;
+    bool floodOnHost = false;      // option "flood=host": run the serial heap flood on a host core
     Exec ex;
     DevBuf<int> ticket;
     Profiler profiler;
@@ -81,6 +82,8 @@ struct Mesh {
     long long E = 0;
     DevBuf<int> off, adj;
     DevBuf<float> xyz, ndist;
+    std::vector<int> hOffCopy, hAdjCopy;       // host CSR for the host-serial stages
+    std::vector<float> hXyzCopy;
     Prims prims;
     StageTimer timer;
 
@@ -111,6 +114,7 @@ struct Mesh {
         for (int r = 0; r < n; r++) if (hOff[r + 1] < hOff[r]) throw Error("adjOffset must be non-decreasing");
         E = hOff[n];
         for (long long i = 0; i < E; i++) if (hAdj[i] < 0 || hAdj[i] >= n) throw Error("adjList entry out of range");
+        hOffCopy.assign(hOff, hOff + n + 1); hAdjCopy.assign(hAdj, hAdj + E); hXyzCopy.assign(hXyz, hXyz + 3 * (size_t)n);
         const Exec& ex = ctx->ex;
         dev_copy(off.ensure(n + 1), hOff, sizeof(int) * (size_t)(n + 1), 0, ex.stream);
         dev_copy(adj.ensure(E), hAdj, sizeof(int) * (size_t)E, 0, ex.stream);
@@ -234,6 +238,29 @@ struct Mesh {
             fprintf(stderr, "[pb] flood: max heap %d (%d entries fit in shared memory)\n", lastMaxHeap, cap);
         }
     }
+    // option flood=host: the serial pass on one host core (arrays round-trip over PCIe, ~17 B/cell)
+    std::vector<float> hfElev, hfSurface, hfKey0, hfKey;
+    std::vector<int> hfDrain, hfSeeds, hfHeap;
+    std::vector<uint8_t> hfVisited;
+    void flood_heap_on_host(const float* elev) {
+        const Exec& x = ex();
+        hfElev.resize(N); hfSurface.resize(N); hfKey0.resize(N); hfDrain.resize(N); hfVisited.resize(N); hfSeeds.resize(N);
+        int nSeeds = 0;
+        dev_copy(&nSeeds, counters.p + 0, sizeof(int), 1, x.stream);
+        dev_copy(hfElev.data(), elev, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfSurface.data(), surface.p, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfKey0.data(), key.p, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfDrain.data(), drainTo.p, sizeof(int) * (size_t)N, 1, x.stream);
+        dev_copy(hfVisited.data(), visited.p, (size_t)N, 1, x.stream);
+        stream_sync(x.stream);
+        dev_copy(hfSeeds.data(), seeds.p, sizeof(int) * (size_t)nSeeds, 1, x.stream);
+        stream_sync(x.stream);
+        flood_heap_host(N, hOffCopy.data(), hAdjCopy.data(), hfElev.data(), hfSurface.data(), hfKey0.data(), hfDrain.data(),
+                        hfVisited.data(), hfSeeds.data(), nSeeds, hfHeap, hfKey);
+        dev_copy(surface.p, hfSurface.data(), sizeof(float) * (size_t)N, 0, x.stream);
+        dev_copy(drainTo.p, hfDrain.data(), sizeof(int) * (size_t)N, 0, x.stream);
+        stream_sync(x.stream);
+    }
     // pass 2: binary lifting over the flood forest, one CTA per flood tree (pb_flood.h)
     void carve_lift_cuda(float* elev, const uint8_t* isOcean, double carveStrength) {
         const Exec& x = ex();
@@ -280,7 +307,8 @@ struct Mesh {
         seeds.ensure(N); heap.ensure(N);
         prims.compact_flagged(x, seedFlag.p, N, seeds.p, counters.p + 0);
 #if PB_CUDA
-        flood_heap_cuda(elev);
+        if (ctx->floodOnHost) flood_heap_on_host(elev);
+        else flood_heap_cuda(elev);
 #else
         x.single(FloodSerialK{g, elev, surface.p, key.p, drainTo.p, visited.p, seeds.p, counters.p + 0, heap.p});
 #endif

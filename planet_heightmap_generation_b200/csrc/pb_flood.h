@@ -164,6 +164,69 @@ struct FloodSerialK {
     }
 };
 
+// Host form of pass 1 (plain C++, both builds).  The CUDA engine can run this stage on a host core
+// instead of the one-CTA kernel (context option "flood=host"): the pass is one serial chain of heap
+// operations, which a CPU core executes ~6x faster than a single GPU warp.  Same MinHeap semantics.
+inline void flood_heap_host(int N, const int* off, const int* adj, const float* elev, float* surface, const float* key0,
+                            int* drainTo, uint8_t* visited, const int* seeds, int nSeeds, std::vector<int>& heap,
+                            std::vector<float>& key) {
+    key.assign(key0, key0 + N);
+    heap.clear();
+    auto push = [&](int cell) {
+        heap.push_back(cell);
+        size_t i = heap.size() - 1;
+        const float kc = key[cell];
+        while (i > 0) {
+            const size_t p = (i - 1) >> 1;
+            const int pc = heap[p];
+            if (kc >= key[pc]) break;
+            heap[i] = pc; heap[p] = cell;
+            i = p;
+        }
+    };
+    for (int s = 0; s < nSeeds; s++) push(seeds[s]);
+    while (!heap.empty()) {
+        const int r = heap[0];
+        const int last = heap.back();
+        heap.pop_back();
+        const size_t n = heap.size();
+        if (n > 0) {
+            heap[0] = last;
+            const float kl = key[last];
+            size_t i = 0;
+            for (;;) {
+                size_t smallest = i; float ks = kl;
+                const size_t l = 2 * i + 1, rr = l + 1;
+                if (l < n) { const float k = key[heap[l]]; if (k < ks) { smallest = l; ks = k; } }
+                if (rr < n) { const float k = key[heap[rr]]; if (k < ks) { smallest = rr; ks = k; } }
+                if (smallest == i) break;
+                heap[i] = heap[smallest]; heap[smallest] = last;
+                i = smallest;
+            }
+        }
+        const double surfR = surface[r];
+        for (int j = off[r], e = off[r + 1]; j < e; j++) {
+            const int nb = adj[j];
+            if (visited[nb]) continue;
+            visited[nb] = 1;
+            drainTo[nb] = r;
+            if ((double)elev[nb] < surfR + PB_FLOOD_EPS) {
+                const float s = (float)(surfR + PB_FLOOD_EPS);
+                surface[nb] = s;
+                // key0 = f32(elev + noise) is not enough here: recompute from the filled surface
+                const double p1 = (double)nb * 2654435761.0;
+                uint32_t h = (uint32_t)(unsigned long long)p1;
+                const int32_t x1 = (int32_t)((h >> 16) ^ h);
+                const double p2 = (double)x1 * 73244475.0;
+                h = (uint32_t)(unsigned long long)(long long)p2;
+                h = (h >> 16) ^ h;
+                key[nb] = (float)((double)s + ((double)h / 4294967295.0) * 0.01);
+            }
+            push(nb);
+        }
+    }
+}
+
 // ---- (2) carve ----------------------------------------------------------------------------------
 // root of each flooded land cell = the coastal seed its drainTo chain ends at (-1: never flooded)
 struct FloodRootK {

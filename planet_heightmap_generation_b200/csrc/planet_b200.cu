@@ -76,6 +76,17 @@ pb_status pb_synchronize(pb_context* ctx) {
     return guard([&] { need(ctx, "ctx is NULL"); ctx->c.bind(); pb::stream_sync(ctx->c.ex.stream); });
 }
 
+pb_status pb_set_option(pb_context* ctx, const char* name, const char* value) {
+    return guard([&] {
+        need(ctx && name && value, "NULL argument");
+        const std::string n = name, v = value;
+        if (n == "flood") {
+            need(v == "device" || v == "host", "flood must be 'device' or 'host'");
+            ctx->c.floodOnHost = v == "host";
+        } else throw std::invalid_argument("unknown option: " + n);
+    });
+}
+
 pb_status pb_profile_start(pb_context* ctx, const char* filter) {
     return guard([&] { need(ctx, "ctx is NULL"); ctx->c.bind(); ctx->c.profiler.start(filter); });
 }

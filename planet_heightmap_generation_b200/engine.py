@@ -96,6 +96,10 @@ class DeviceMesh:
             return torch.empty(n, dtype=dt, device=like.device)
         return np.empty(n, _NP[kind])
 
+    def set_option(self, name: str, value: str):
+        """Engine options, e.g. ("flood", "host" | "device")."""
+        self.lib.check(self.lib.dll.pb_set_option(self._ctx, name.encode(), value.encode()))
+
     def synchronize(self):
         self.lib.check(self.lib.dll.pb_synchronize(self._ctx))
 

@@ -112,3 +112,41 @@ def synthetic_plates(r_xyz: np.ndarray, elevation: np.ndarray, seed: int, n_plat
     size = np.bincount(owner, minlength=n_plates)
     plate_is_ocean = {int(seeds[k]) for k in range(n_plates) if below[k] > 0.5 * size[k]}
     return r_plate, plate_is_ocean
+
+
+def synthetic_plate_tables(r_xyz: np.ndarray, elevation: np.ndarray, seed: int, n_plates: int = 40, n_super: int = 10):
+    """Seeded stand-ins for the plate pipeline's outputs read by assignElevation (js/planet-worker.js:176-216):
+    r_plate, plate table {pid: isOcean, pole, omega, density} in plateSeeds order, and superPlateData
+    (r_superPlate + super-plate table).  Poles are random unit vectors, omega in ±[0.5, 1.5], densities as the
+    worker draws them (3.0–3.5 oceanic, 2.4–2.9 continental)."""
+    r_plate, pio = synthetic_plates(r_xyz, elevation, seed, n_plates)
+    rng = np.random.default_rng(seed + 104729)
+    ids = [int(p) for p in np.unique(r_plate)]
+    rng.shuffle(ids)                                   # plateSeeds is a Set: insertion order is not sorted
+    plates = {}
+    for pid in ids:
+        pole = rng.normal(size=3)
+        pole /= np.linalg.norm(pole)
+        oc = pid in pio
+        plates[pid] = dict(isOcean=oc, pole=tuple(float(v) for v in pole),
+                           omega=float(rng.uniform(0.5, 1.5) * rng.choice([-1, 1])),
+                           density=float((3.0 if oc else 2.4) + rng.uniform(0, 0.5)))
+    # super plates: group plates by nearest of n_super random directions
+    p = np.asarray(r_xyz, np.float32).reshape(-1, 3)
+    centers = rng.normal(size=(n_super, 3))
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    plate_center = {pid: p[pid].astype(np.float64) for pid in ids}
+    group = {pid: int(np.argmax(centers @ plate_center[pid])) for pid in ids}
+    super_plates = {}
+    for g in sorted(set(group.values())):
+        members = [pid for pid in ids if group[pid] == g]
+        pole = rng.normal(size=3)
+        pole /= np.linalg.norm(pole)
+        oc = sum(plates[m]["isOcean"] for m in members) * 2 > len(members)
+        super_plates[g] = dict(isOcean=oc, pole=tuple(float(v) for v in pole), omega=float(rng.uniform(0.5, 1.5) * rng.choice([-1, 1])),
+                               density=float(np.mean([plates[m]["density"] for m in members])))
+    lut = np.zeros(int(max(ids)) + 1, np.int32)
+    for pid in ids:
+        lut[pid] = group[pid]
+    r_super = lut[r_plate].astype(np.int32)
+    return r_plate, plates, ids, r_super, super_plates

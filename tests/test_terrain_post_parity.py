@@ -87,6 +87,25 @@ def test_priority_flood_carve_large(oracle, cuda_lib):
     assert_bit_equal(got, want, "priorityFloodCarve elevation")
 
 
+@pytest.mark.gpu
+def test_flood_on_host_option_matches(oracle, cuda_lib, planet_medium):
+    """Option flood=host (the serial heap pass on a host core, the rest on the GPU) gives identical results."""
+    from planet_heightmap_generation_b200.terrain_post import priorityFloodCarve
+    mesh, xyz, nd, elev = planet_medium()
+    ocean = (elev <= 0).astype(np.uint8)
+    want = elev.copy()
+    o_drain, o_surf, o_open = oracle.priority_flood_carve(mesh, want, ocean, 0.5)
+    dm = _dm(cuda_lib, mesh, xyz)
+    dm.set_option("flood", "host")
+    got = elev.copy()
+    drain, surf, openo = priorityFloodCarve(dm, got, ocean, 0.5, taps=True)
+    assert_bit_equal(drain, o_drain, "drainTo")
+    assert_bit_equal(surf, o_surf, "surface")
+    assert_bit_equal(got, want, "elevation")
+    with pytest.raises(Exception):
+        dm.set_option("flood", "nowhere")
+
+
 def test_flood_with_inland_sea_and_island(backend, oracle, planet_small):
     """Second-largest ocean component is an inland sea (not a flood seed); an island inside it is never flooded."""
     from planet_heightmap_generation_b200.terrain_post import priorityFloodCarve
