@@ -140,6 +140,32 @@ pb_status pb_last_post_timing(pb_mesh* mesh, double* ms_out);
 /* smoothField(mesh, field, passes)                                    js/climate-util.js:5-25 */
 pb_status pb_smooth_field(pb_mesh* mesh, float* field, int32_t passes);
 
+/* ---- elevation (js/elevation.js) --------------------------------------------------------------------------
+ * assignElevation(mesh, r_xyz, plateIsOcean, r_plate, plateVec, plateSeeds, noise, noiseMag, seed, spread,
+ *                 plateDensity, superPlateData) → {r_elevation, mountain_r, coastline_r, ocean_r, r_stress,
+ *                 debugLayers}                                                       js/elevation.js:216-1391
+ * The JS objects keyed by plate id (plateVec {pid:{pole,omega}}, plateDensity {pid:d}) and the plateIsOcean Set
+ * arrive as one table with a row per plate (host arrays, any order).  plateSeeds is the Set's iteration order.
+ * superPlates == NULL means superPlateData == null (js/planet-worker.js:207-211).  The three region Sets come
+ * back as membership masks.  debug[] order: base, tectonic, noise, interior, coastal, ocean, hotspot,
+ * tecActivity, margins, backArc, foldRidge, orogenicPower (js/elevation.js:1386); any entry may be NULL.
+ * `noiseSeed` seeds the caller's SimplexNoise instance (new SimplexNoise(seed), js/planet-worker.js:203).
+ * Per-cell arrays follow the context's pointer mode; the plate tables are always host arrays.
+ * The order-dependent middle of the function (stress propagation, the five randomized distance fills, the
+ * capped FIFO BFS with payloads, the RNG-placed hotspot domes — SURVEY.md classes R/F/S) runs on host threads
+ * inside this call; collisions and all per-cell synthesis run as CUDA kernels. */
+typedef struct pb_plate_table {
+    int32_t n; const int32_t* ids; const uint8_t* isOcean; const double* pole /* 3n */; const double* omega;
+    const double* density;
+} pb_plate_table;
+typedef struct pb_elevation_result {
+    float* r_elevation; float* r_stress; uint8_t* mountain_r; uint8_t* coastline_r; uint8_t* ocean_r; float* debug[12];
+} pb_elevation_result;
+pb_status pb_assign_elevation(pb_mesh* mesh, const pb_plate_table* plates, const int32_t* r_plate,
+                              const int32_t* plateSeeds, int32_t numPlateSeeds, double noiseSeed, double noiseMag,
+                              double seed, double spread, const pb_plate_table* superPlates,
+                              const int32_t* r_superPlate, const pb_elevation_result* out);
+
 /* ---- climate (js/wind.js, js/ocean.js, js/precipitation.js, js/heuristic-precip.js, js/temperature.js,
  * js/koppen.js) ------------------------------------------------------------------------------------------
  * A pb_climate holds the reference's result objects (windResult, oceanResult, precipResult, tempResult —

@@ -55,6 +55,7 @@ SYMBOLS = {
     "pb_run_post_processing": (C.c_int, [_vp, _vp, C.POINTER(PostParams), _dbl, _vp, _vp, _vp]),
     "pb_last_post_timing": (C.c_int, [_vp, _vp]),
     "pb_smooth_field": (C.c_int, [_vp, _vp, _i32]),
+    "pb_assign_elevation": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "pb_climate_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "pb_climate_destroy": (None, [_vp]),
     "pb_compute_wind": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _dbl, _dbl]),
@@ -66,6 +67,16 @@ SYMBOLS = {
     "pb_climate_field_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32), C.POINTER(_i64)]),
     "pb_climate_get": (C.c_int, [_vp, C.c_char_p, _vp]),
 }
+
+
+class PlateTable(C.Structure):
+    _fields_ = [("n", C.c_int32), ("ids", C.c_void_p), ("isOcean", C.c_void_p), ("pole", C.c_void_p), ("omega", C.c_void_p),
+                ("density", C.c_void_p)]
+
+
+class ElevationResult(C.Structure):
+    _fields_ = [("r_elevation", C.c_void_p), ("r_stress", C.c_void_p), ("mountain_r", C.c_void_p), ("coastline_r", C.c_void_p),
+                ("ocean_r", C.c_void_p), ("debug", C.c_void_p * 12)]
 
 
 class Library:

@@ -3,6 +3,8 @@
 // test-only host emulation used by the CPU test-suite (tests/emul/).
 #include "pb_engine.h"
 #include "pb_climate_engine.h"
+#include "pb_elevation_engine.h"
+#include <memory>
 #include <cxxabi.h>
 
 namespace {
@@ -32,6 +34,7 @@ void need(bool c, const char* what) {
 struct pb_context { pb::Context c; explicit pb_context(int d) : c(d) {} };
 struct pb_mesh {
     pb::Mesh m;
+    std::unique_ptr<pb::Elevation> elevation;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
 
@@ -258,6 +261,58 @@ pb_status pb_last_post_timing(pb_mesh* mesh, double* ms) {
         mesh->m.ctx->bind();
         mesh->m.timer.resolve();
         for (int i = 0; i < 5; i++) ms[i] = mesh->m.timer.ms[i];
+    });
+}
+
+// ---- elevation ---------------------------------------------------------------------------------------------
+pb_status pb_assign_elevation(pb_mesh* mesh, const pb_plate_table* plates, const int32_t* r_plate, const int32_t* plateSeeds,
+                              int32_t nSeeds, double noiseSeed, double noiseMag, double seed, double spread,
+                              const pb_plate_table* superPlates, const int32_t* r_superPlate, const pb_elevation_result* out) {
+    return guard([&] {
+        need(mesh && plates && r_plate && out && out->r_elevation && (plateSeeds || nSeeds == 0) && nSeeds >= 0, "NULL argument");
+        need(!superPlates || r_superPlate, "superPlates given without r_superPlate");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        if (!mesh->elevation) mesh->elevation.reset(new pb::Elevation(&m));
+        pb::Elevation& E = *mesh->elevation;
+        const size_t N = (size_t)m.N;
+        pb::PlateTableHost P, SP;
+        P.set(plates->n, plates->ids, plates->isOcean, plates->pole, plates->omega, plates->density);
+        if (superPlates) SP.set(superPlates->n, superPlates->ids, superPlates->isOcean, superPlates->pole, superPlates->omega, superPlates->density);
+        // r_plate / r_superPlate: one device copy for the kernels, one host copy for the host-serial stages
+        std::vector<int> hPlate(N), hSuper;
+        const int* dPlate; const int* dSuper = nullptr;
+        if (m.hostMode()) {
+            memcpy(hPlate.data(), r_plate, sizeof(int) * N);
+            dPlate = m.arg_in(r_plate, N, E.sPlate);
+            if (superPlates) { hSuper.assign(r_superPlate, r_superPlate + N); dSuper = m.arg_in(r_superPlate, N, E.sSuper); }
+        } else {
+            dPlate = r_plate;
+            pb::dev_copy(hPlate.data(), r_plate, sizeof(int) * N, 1, m.ex().stream);
+            if (superPlates) { hSuper.resize(N); dSuper = r_superPlate; pb::dev_copy(hSuper.data(), r_superPlate, sizeof(int) * N, 1, m.ex().stream); }
+            pb::stream_sync(m.ex().stream);
+        }
+        for (size_t r = 0; r < N; r++) if (P.find(hPlate[r]) < 0) throw std::invalid_argument("r_plate holds an id that is not in the plate table");
+        if (superPlates) for (size_t r = 0; r < N; r++) if (SP.find(hSuper[r]) < 0) throw std::invalid_argument("r_superPlate holds an id that is not in the super-plate table");
+        pb::ElevationOutputs o;
+        o.elev = m.arg_out(out->r_elevation, N, E.sElevOut);
+        o.stress = out->r_stress ? m.arg_out(out->r_stress, N, E.sStressOut) : E.sStressOut.ensure(N);
+        o.mountain = m.arg_out(out->mountain_r, N, E.sM);
+        o.coastline = m.arg_out(out->coastline_r, N, E.sC);
+        o.ocean = m.arg_out(out->ocean_r, N, E.sO);
+        float** dbg[12] = {&o.dbg.base, &o.dbg.tectonic, &o.dbg.noise, &o.dbg.interior, &o.dbg.coastal, &o.dbg.ocean, &o.dbg.hotspot,
+                           &o.dbg.tecActivity, &o.dbg.margins, &o.dbg.backArc, &o.dbg.foldRidge, &o.dbg.orogenicPower};
+        for (int k = 0; k < 12; k++)
+            *dbg[k] = (out->debug[k] && !m.hostMode()) ? out->debug[k] : E.sDbg[k].ensure(N);
+        std::vector<int> seeds(plateSeeds, plateSeeds + nSeeds);
+        E.assign(P, dPlate, hPlate.data(), seeds, noiseSeed, noiseMag, seed, spread, superPlates ? &SP : nullptr, dSuper,
+                 superPlates ? hSuper.data() : nullptr, o);
+        m.arg_back(out->r_elevation, o.elev, N);
+        m.arg_back(out->r_stress, o.stress, N);
+        m.arg_back(out->mountain_r, o.mountain, N);
+        m.arg_back(out->coastline_r, o.coastline, N);
+        m.arg_back(out->ocean_r, o.ocean, N);
+        for (int k = 0; k < 12; k++) if (out->debug[k]) m.arg_back(out->debug[k], *dbg[k], N);
+        m.finish();
     });
 }
 
