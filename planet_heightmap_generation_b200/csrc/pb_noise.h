@@ -40,12 +40,12 @@ struct SimplexTable {
 struct Simplex {
     const uint8_t* tab;
 
-    PB_DEV int P(int i) const { return tab[i]; }
-    PB_DEV int M(int i) const { return tab[512 + i]; }
+    PB_HDEV int P(int i) const { return tab[i]; }
+    PB_HDEV int M(int i) const { return tab[512 + i]; }
 
     // gradient g·(x,y,z) with the reference's table order (js/simplex-noise.js:7); the products by
     // 0/±1 are kept so that signed zeros come out as in JS.
-    static PB_DEV double gdot(int g, double x, double y, double z) {
+    static PB_HDEV double gdot(int g, double x, double y, double z) {
         const double s1 = (g & 1) ? -1.0 : 1.0;
         const double s2 = (g & 2) ? -1.0 : 1.0;
         const int grp = g >> 2;
@@ -56,7 +56,7 @@ struct Simplex {
         return v0 * x + v1 * y + v2 * z;
     }
 
-    static PB_DEV double corner(double x, double y, double z, int g) {
+    static PB_HDEV double corner(double x, double y, double z, int g) {
         double a = 0.6 - x * x - y * y - z * z;
         if (a > 0) {
             a *= a;
@@ -66,7 +66,7 @@ struct Simplex {
     }
 
     // js/simplex-noise.js:17-32
-    PB_DEV double noise3D(double x, double y, double z) const {
+    PB_HDEV double noise3D(double x, double y, double z) const {
         const double F = 1.0 / 3.0, H = 1.0 / 6.0;
         const double s = (x + y + z) * F;
         const double i = floor(x + s), j = floor(y + s), k = floor(z + s);
@@ -97,7 +97,7 @@ struct Simplex {
     }
 
     // js/simplex-noise.js:34-38
-    PB_DEV double fbm(double x, double y, double z, int octaves, double persistence) const {
+    PB_HDEV double fbm(double x, double y, double z, int octaves, double persistence) const {
         double sum = 0, mx = 0, amp = 1;
         for (int o = 0; o < octaves; o++) {
             const double f = (double)(1 << o);
@@ -107,10 +107,10 @@ struct Simplex {
         }
         return sum / mx;
     }
-    PB_DEV double fbm(double x, double y, double z, int octaves) const { return fbm(x, y, z, octaves, 2.0 / 3.0); }
+    PB_HDEV double fbm(double x, double y, double z, int octaves) const { return fbm(x, y, z, octaves, 2.0 / 3.0); }
 
     // js/simplex-noise.js:40-53
-    PB_DEV double ridgedFbm(double x, double y, double z, int octaves, double lacunarity, double gain,
+    PB_HDEV double ridgedFbm(double x, double y, double z, int octaves, double lacunarity, double gain,
                             double offset) const {
         double sum = 0, freq = 1, amp = 1, prev = 1, maxVal = 0;
         for (int o = 0; o < octaves; o++) {
@@ -125,7 +125,7 @@ struct Simplex {
         }
         return sum / maxVal;
     }
-    PB_DEV double ridgedFbm(double x, double y, double z) const { return ridgedFbm(x, y, z, 6, 2.0, 0.5, 1.0); }
+    PB_HDEV double ridgedFbm(double x, double y, double z) const { return ridgedFbm(x, y, z, 6, 2.0, 0.5, 1.0); }
 };
 
 }  // namespace pb

@@ -25,10 +25,12 @@
 #define PB_CUDA 1
 #include <cuda_runtime.h>
 #define PB_DEV __device__ __forceinline__
+#define PB_HDEV __host__ __device__ __forceinline__
 #define PB_GLOBAL __global__
 #else
 #define PB_CUDA 0
 #define PB_DEV inline
+#define PB_HDEV inline
 typedef void* cudaStream_t;
 #endif
 
