@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — Voronoi cells/s of the per-cell hot path (BASELINE.json: full pipeline erosion→climate).
+"""bench.py — Voronoi cells/s of the per-cell hot path (BASELINE.json: full pipeline elevation→erosion→climate).
 
 A "step" is one pass over a 1 000 001-cell Fibonacci-sphere Voronoi mesh (seed 42, sliders at the
-reference's UI defaults):
+reference's UI defaults, P = 40 plates in 10 super-plates):
 
-  --workload full (default, BASELINE configs[2]) = post + climate
+  --workload full (default, BASELINE configs[2]) = elevation + post + climate, i.e. handleGenerate
+                     (js/planet-worker.js:136-339) from assignElevation on
   --workload post    (configs[1])  reapply-style pass (js/planet-worker.js:341-358): clone the pre-erosion
                      elevation, runPostProcessing = warp → smooth → erodeComposite (50 stream-power iterations,
                      5 glacial, 1 thermal, two priority floods) → ridge sharpening → soil creep → erosionDelta
   --workload climate computeWind → computeOceanCurrents → computePrecipitation → computeTemperature →
                      classifyKoppen on the eroded elevation (js/planet-worker.js:229-268)
+  --workload elevation   assignElevation alone (js/elevation.js:216-1391)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--cells C] [--workload W]
 
@@ -79,21 +81,34 @@ def get_planet(cells: int, seed: int = SEED):
     return mesh, xyz
 
 
-def get_inputs(cells: int, seed: int = SEED):
-    """mesh, r_xyz, pre-erosion elevation, r_plate, plateIsOcean — the inputs the hot path receives from the
-    upstream stages (mesh construction, plates, assignElevation), here seeded synthetic stand-ins."""
-    from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plates
-    mesh, xyz = get_planet(cells, SEED)
-    elev0 = synthetic_elevation(xyz, seed, 0.3)
-    r_plate, pio = synthetic_plates(xyz, elev0, seed)
-    return mesh, xyz, elev0, r_plate, pio
+NMAG, SPREAD = 0.40, 5       # Roughness slider default (index.html) and the worker's fixed spread (planet-worker.js:138)
+
+
+class Inputs:
+    """What the hot path receives from the upstream stages (mesh construction, plate pipeline): mesh, r_xyz and
+    the plate tables — here seeded synthetic stand-ins (sphere.synthetic_plate_tables)."""
+
+    def __init__(self, cells: int, seed: int = SEED):
+        from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plate_tables
+        self.mesh, self.xyz = get_planet(cells, SEED)
+        hint = synthetic_elevation(self.xyz, seed, 0.3)       # only decides which plates are oceanic
+        self.r_plate, self.plates, self.seeds, self.r_super, self.super_plates = synthetic_plate_tables(self.xyz, hint, seed)
+        self.pio = {p for p, v in self.plates.items() if v["isOcean"]}
+        self.vec = {p: {"pole": v["pole"], "omega": v["omega"]} for p, v in self.plates.items()}
+        self.dens = {p: v["density"] for p, v in self.plates.items()}
+        sp = self.super_plates
+        self.super_data = lambda r_super: {
+            "r_superPlate": r_super, "superPlateIsOcean": {p for p, v in sp.items() if v["isOcean"]},
+            "superPlateVec": {p: {"pole": v["pole"], "omega": v["omega"]} for p, v in sp.items()},
+            "superPlateDensity": {p: v["density"] for p, v in sp.items()}}
 
 
 def workload_name(cells, hiters, workload):
+    elev = "assignElevation (40 plates, 10 super-plates, nMag 0.40, spread 5)"
     post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
             f"ridge 3, creep 3")
     clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
-    what = {"post": post, "climate": clim, "full": post + " then " + clim}[workload]
+    what = {"post": post, "climate": clim, "elevation": elev, "full": elev + " then " + post + " then " + clim}[workload]
     return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
 
 
@@ -161,27 +176,42 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline; never the product path)
 # ---------------------------------------------------------------------------------------------------
-def oracle_step_seconds(inputs, hiters, steps, warmup, workload):
+def oracle_step_seconds(inp, hiters, steps, warmup, workload):
+    """Times the oracle on the same workload.  Returns (per-step seconds, per-stage seconds of the last step)."""
     from oracle import binding as oracle
     oracle.build()
-    mesh, xyz, elev0, r_plate, pio = inputs
+    mesh, xyz = inp.mesh, inp.xyz
     nd = oracle.neighbor_dist(mesh, xyz)
-    clim = oracle.Climate(mesh, xyz) if workload != "post" else None
-    e_clim = elev0.copy()
-    if workload == "climate":   # climate runs on the eroded planet: erode once, untimed
-        oracle.run_post_processing(mesh, xyz, e_clim, SLIDERS, nd, SEED, None, hiters)
-    times = []
+    oe = oracle.Elevation(mesh, xyz)
+    clim = oracle.Climate(mesh, xyz)
+
+    def elevation():
+        oe.assign(inp.r_plate, inp.plates, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.r_super, inp.super_plates)
+        return oe.get("r_elevation"), oe.get("hotspot")
+
+    pre = hot = eroded = None
+    if workload in ("post", "climate"):
+        pre, hot = elevation()
+    if workload == "climate":
+        eroded = pre.copy()
+        oracle.run_post_processing(mesh, xyz, eroded, SLIDERS, nd, SEED, hot, hiters)
+    times, stages = [], {}
     for i in range(warmup + steps):
-        e = elev0.copy() if workload != "climate" else e_clim
         t = time.perf_counter()
-        if workload != "climate":
-            oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, None, hiters)
-        if workload != "post":
-            clim.run_all(e, pio, r_plate, SEED)
-        dt = time.perf_counter() - t
+        e, h = (pre.copy(), hot) if pre is not None else (None, None)
+        if workload in ("full", "elevation"):
+            e, h = elevation()
+        t1 = time.perf_counter()
+        if workload in ("full", "post"):
+            oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, h, hiters)
+        t2 = time.perf_counter()
+        if workload in ("full", "climate"):
+            clim.run_all(eroded if workload == "climate" else e, inp.pio, inp.r_plate, SEED)
+        t3 = time.perf_counter()
         if i >= warmup:
-            times.append(dt)
-    return times
+            times.append(t3 - t)
+        stages = {"elevation_s": t1 - t, "post_s": t2 - t1, "climate_s": t3 - t2}
+    return times, stages
 
 
 def cpu_model():
@@ -198,9 +228,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    inputs = get_inputs(args.cells)
-    n = inputs[0].numRegions
-    times = oracle_step_seconds(inputs, args.hiters, args.steps, args.warmup, args.workload)
+    inp = Inputs(args.cells)
+    n = inp.mesh.numRegions
+    times, stages = oracle_step_seconds(inp, args.hiters, args.steps, args.warmup, args.workload)
     total = float(np.sum(times))
     v = n * len(times) / total
     sample = f"full workload, {len(times)} timed passes of {n} cells after {args.warmup} warm-up"
@@ -212,7 +242,7 @@ def run_reference(args):
                    "note": "reference is browser JavaScript (one Web Worker, single thread); no JS runtime in this image, "
                            "so this arm times oracle/ — the C++ -O2 restatement of the same functions — on one host core"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "cpu": cpu_model(), "host_cores": os.cpu_count()},
+                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages_last_step": stages},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -255,6 +285,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from planet_heightmap_generation_b200 import climate as cl
+    from planet_heightmap_generation_b200.elevation import DEBUG_LAYERS, assignElevation
     from planet_heightmap_generation_b200.engine import DeviceMesh
     from planet_heightmap_generation_b200.terrain_post import runPostProcessing
 
@@ -270,35 +301,49 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     wl = args.workload
-    do_post, do_clim = wl != "climate", wl != "post"
-    # replicas: every rank processes its own planet (same mesh, different terrain seed)
-    mesh, xyz, elev0_h, r_plate_h, pio = get_inputs(args.cells, SEED + rank)
+    do_elev, do_post, do_clim = wl in ("full", "elevation"), wl in ("full", "post"), wl in ("full", "climate")
+    # replicas: every rank processes its own planet (same mesh, different plates / terrain seed)
+    inp = Inputs(args.cells, SEED + rank)
+    mesh, xyz = inp.mesh, inp.xyz
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
-    land = int((elev0_h > 0).sum())
     dm = DeviceMesh(mesh, xyz, device=local)
+    if args.flood:
+        dm.set_option("flood", args.flood)
 
-    elev0 = torch.from_numpy(elev0_h).to(dev)
-    r_plate = torch.from_numpy(r_plate_h).to(dev)
-    elev = torch.empty_like(elev0)
-    delta = torch.empty_like(elev0)
+    r_plate = torch.from_numpy(inp.r_plate).to(dev)
+    r_super = torch.from_numpy(inp.r_super).to(dev)
+    delta = torch.empty(N, dtype=torch.float32, device=dev)
     ocean = torch.empty(N, dtype=torch.uint8, device=dev)
     koppen = torch.empty(N, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    state = {}
+
+    def elevation_device():
+        res = assignElevation(dm, None, inp.pio, r_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
+                              inp.super_data(r_super))
+        state["elev"], state["hotspot"] = res["r_elevation"], res["debugLayers"]["hotspot"]
 
     def post_device():
-        elev.copy_(elev0)    # handleReapply clones W.prePostElev before post-processing (planet-worker.js:353)
-        runPostProcessing(dm, None, elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
+        runPostProcessing(dm, None, state["elev"], SLIDERS, None, SEED, state["hotspot"], hItersOverride=args.hiters,
                           out_erosionDelta=delta, out_isOcean=ocean, timing=False)
 
-    if not do_post:          # climate-only: the eroded planet is the (untimed) input
+    # untimed preparation of the inputs the chosen workload starts from
+    elevation_device()
+    pre = state["elev"].clone()
+    land = int((pre > 0).sum().item())
+    if wl == "climate":
         post_device()
 
     def step_device():
         flush.zero_()
+        if do_elev:
+            elevation_device()
+        elif do_post:
+            state["elev"] = pre.clone()   # handleReapply clones W.prePostElev before post-processing (planet-worker.js:353)
         if do_post:
             post_device()
         if do_clim:
-            cl.computeClimate(dm, elev, pio, r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
+            cl.computeClimate(dm, state["elev"], inp.pio, r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
 
     def barrier():
         torch.cuda.synchronize()
@@ -350,32 +395,40 @@ def run_b200(args):
     value = N * world * args.steps / (ms_total / 1000.0)
 
     # ---- end to end through the host-pointer C ABI ------------------------------------------------
-    h_elev0 = torch.from_numpy(elev0_h).pin_memory()
-    h_plate = torch.from_numpy(r_plate_h).pin_memory()
+    elev_dev_final = state["elev"].clone()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_plate, h_super, h_pre, h_hot0 = pin(inp.r_plate), pin(inp.r_super), pin(pre.cpu().numpy()), pin(state["hotspot"].cpu().numpy())
     h_elev = torch.empty(N, dtype=torch.float32).pin_memory()
     h_delta = torch.empty(N, dtype=torch.float32).pin_memory()
     h_ocean = torch.empty(N, dtype=torch.uint8).pin_memory()
     h_koppen = torch.empty(N, dtype=torch.uint8).pin_memory()
-    np_elev, np_delta, np_ocean, np_koppen, np_plate = (h_elev.numpy(), h_delta.numpy(), h_ocean.numpy(),
-                                                       h_koppen.numpy(), h_plate.numpy())
-    if not do_post:
-        h_elev.copy_(elev.cpu())
-    h2d = (4 * N if do_post else 0) + (8 * N if do_clim else 0)
-    d2h = (9 * N if do_post else 0) + ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
-    reply = {}
+    np_delta, np_ocean, np_koppen, np_plate, np_super = h_delta.numpy(), h_ocean.numpy(), h_koppen.numpy(), h_plate.numpy(), h_super.numpy()
+    if wl == "climate":
+        h_elev.copy_(elev_dev_final.cpu())
+    h2d = (8 * N if do_elev else 0) + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
+    d2h = ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
+          ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
+    reply, host = {}, {}
 
     def step_host():
         flush.zero_()
+        np_elev, np_hot = h_elev.numpy(), h_hot0.numpy()
+        if do_elev:
+            res = assignElevation(dm, None, inp.pio, np_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
+                                  inp.super_data(np_super))
+            np_elev, np_hot = res["r_elevation"], res["debugLayers"]["hotspot"]
+        elif do_post:
+            h_elev.copy_(h_pre)
         if do_post:
-            h_elev.copy_(h_elev0)
-            runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, None, hItersOverride=args.hiters,
+            runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, np_hot, hItersOverride=args.hiters,
                               out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
         if do_clim:
-            w, o, p, t, _ = cl.computeClimate(dm, np_elev, pio, np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
+            w, o, p, t, _ = cl.computeClimate(dm, np_elev, inp.pio, np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
             for res, keys in ((w, CLIMATE_REPLY_F32[:4] + ["itczLons", "itczLatsSummer", "itczLatsWinter"]),
                               (o, CLIMATE_REPLY_F32[4:12]), (p, CLIMATE_REPLY_F32[12:14]), (t, CLIMATE_REPLY_F32[14:])):
                 for k in keys:
                     reply[k] = res[k]     # device → host copy of every array of the climateDone message
+        host["elev"] = np_elev
 
     step_host()
     barrier()
@@ -390,7 +443,8 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = N * world * args.steps / e2e_s
     # host-pointer and device-pointer passes agree bit for bit
-    same = bool((h_elev == elev.cpu()).all().item()) and (not do_clim or bool((h_koppen == koppen.cpu()).all().item()))
+    same = bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item()) and \
+        (not do_clim or bool((h_koppen == koppen.cpu()).all().item()))
 
     # ---- roofline (events recorded inside the timed region) ---------------------------------------------
     peaks = {}
@@ -421,10 +475,10 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        times = oracle_step_seconds((mesh, xyz, elev0_h, r_plate_h, pio), args.hiters, 1, 0, wl)
+        times, stages = oracle_step_seconds(inp, args.hiters, 1, 0, wl)
         cpu_baseline = {"value": N / times[0], "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread",
-                        "cpu": cpu_model(), "host_cores": os.cpu_count()}
+                        "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages": stages}
 
     if rank == 0:
         print(json.dumps({
@@ -435,8 +489,9 @@ def run_b200(args):
                        "multi_gpu": "replicas (one planet per GPU, no data-path collective)" if world > 1 else "single",
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
-                       "inputs": "mesh, pre-erosion elevation and plates are seeded synthetic stand-ins for the upstream "
-                                 "stages (mesh construction, plates, assignElevation), resident before the timed region"},
+                       "flood": args.flood or "device",
+                       "inputs": "mesh and plate tables are seeded synthetic stand-ins for the upstream stages (mesh "
+                                 "construction, plate pipeline), resident before the timed region"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same},
@@ -453,7 +508,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "post", "climate"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation"])
+    ap.add_argument("--flood", default="", choices=["", "device", "host"],
+                    help="engine option: where the serial heap pass of priorityFloodCarve runs (default device)")
     ap.add_argument("--cells", type=int, default=1_000_000)
     ap.add_argument("--hiters", type=int, default=50)
     ap.add_argument("--dominant", default="", help="kernel whose launches are event-timed for the roofline "
