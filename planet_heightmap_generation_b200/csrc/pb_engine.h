@@ -106,6 +106,7 @@ struct Mesh {
     DevBuf<int> order, pos, drainTarget, cnt, k0, k1, k2, iceTarget, kSelf;
     DevBuf<float> cellDist, flow, contrib, glacIdx, iceFlow;
     DevBuf<double> total;
+    DevBuf<unsigned long long> words;
     DevBuf<uint8_t> nUp, kEdge;
 
     Mesh(Context* c, int n, const int* hOff, const int* hAdj, const float* hXyz) : ctx(c), N(n) {
@@ -382,7 +383,7 @@ struct Mesh {
         x.for_each(landCount, PosK{order.p, pos.p});
 
         drainTarget.ensure(N); cellDist.ensure(N); flow.ensure(N); contrib.ensure(N); cnt.ensure(N);
-        k0.ensure(N); k1.ensure(N); k2.ensure(N); tmp.ensure(N); total.ensure(N);
+        k0.ensure(N); k1.ensure(N); k2.ensure(N); tmp.ensure(N); total.ensure(N); words.ensure(N);
 
         if (hIters > 0) priority_flood_carve(elev, isOcean, 0.5, nullptr);
 
@@ -409,9 +410,9 @@ struct Mesh {
 
             if (glacialThisIter) {
                 x.for_each(N, IceReceiversK{g, elev, isOcean, glacIdx.p, iceTarget.p});
-                dev_memset(cnt.p, 0, sizeof(int) * (size_t)N, x.stream);
-                x.ordered(landCount, AccumulateK{g, order.p, pos.p, iceTarget.p, isOcean, glacIdx.p, contrib.p, cnt.p});
-                x.for_each(N, AccumulateFinalK{g, pos.p, iceTarget.p, isOcean, glacIdx.p, contrib.p, iceFlow.p, nUp.p});
+                dev_memset(words.p, 0, sizeof(unsigned long long) * (size_t)N, x.stream);
+                x.ordered(landCount, AccumulateK{g, order.p, pos.p, iceTarget.p, isOcean, glacIdx.p, words.p});
+                x.for_each(N, AccumulateFinalK{g, pos.p, iceTarget.p, isOcean, glacIdx.p, words.p, iceFlow.p, nUp.p});
                 dev_memset(cnt.p, 0, sizeof(int) * (size_t)N, x.stream);
                 x.for_each(N, CarvePrepK{g, pos.p, isOcean, iceFlow.p, kSelf.p, kEdge.p});
                 x.ordered(landCount, CarveK{g, order.p, isOcean, ndist.p, iceFlow.p, nUp.p, elev, cnt.p, kSelf.p, kEdge.p,
@@ -423,9 +424,9 @@ struct Mesh {
             if (hydraulicThisIter) {
                 if (glacialThisIter) sort_land_desc(elev, landCount);
                 x.for_each(N, ReceiversK{g, elev, isOcean, ndist.p, drainTarget.p, cellDist.p});
-                dev_memset(cnt.p, 0, sizeof(int) * (size_t)N, x.stream);
-                x.ordered(landCount, AccumulateK{g, order.p, pos.p, drainTarget.p, isOcean, nullptr, contrib.p, cnt.p});
-                x.for_each(N, AccumulateFinalK{g, pos.p, drainTarget.p, isOcean, nullptr, contrib.p, flow.p, nullptr});
+                dev_memset(words.p, 0, sizeof(unsigned long long) * (size_t)N, x.stream);
+                x.ordered(landCount, AccumulateK{g, order.p, pos.p, drainTarget.p, isOcean, nullptr, words.p});
+                x.for_each(N, AccumulateFinalK{g, pos.p, drainTarget.p, isOcean, nullptr, words.p, flow.p, nullptr});
                 if (taps && iter == taps->captureIter) {
                     if (taps->drainTarget) dev_copy(taps->drainTarget, drainTarget.p, sizeof(int) * (size_t)N, 2, x.stream);
                     if (taps->flow) dev_copy(taps->flow, flow.p, sizeof(float) * (size_t)N, 2, x.stream);
@@ -434,10 +435,11 @@ struct Mesh {
                         dev_copy(taps->landOrder, order.p, sizeof(int) * (size_t)landCount, 2, x.stream);
                     }
                 }
-                dev_memset(cnt.p, 0, sizeof(int) * (size_t)N, x.stream);
                 x.for_each(N, SolvePrepK{g, pos.p, drainTarget.p, isOcean, k0.p, k1.p, k2.p});
-                x.ordered(landCount, SolveK{order.p, landCount, drainTarget.p, isOcean, cellDist.p, flow.p, elev, cnt.p,
+                x.for_each(N, PackElevK{elev, words.p});
+                x.ordered(landCount, SolveK{order.p, landCount, drainTarget.p, isOcean, cellDist.p, flow.p, elev, words.p,
                                             k0.p, k1.p, k2.p, K, m, dt});
+                x.for_each(N, UnpackElevK{words.p, isOcean, elev});
             }
 
             if (iter < tIters) {

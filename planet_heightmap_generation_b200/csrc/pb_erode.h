@@ -58,40 +58,35 @@ struct ReceiversK {
 struct AccumulateK {
     Csr g; const int* order; const int* pos; const int* target; const uint8_t* isOcean;
     const float* initv;      // nullptr → 1.0
-    float* contrib; int* cnt;
+    unsigned long long* contrib;     // (value, done) words, cleared before the launch
     PB_DEV bool try_run(int i) const {
         const int r = order[i];
         const int b = g.off[r], e = g.off[r + 1];
-        int need = 0;
-        for (int j = b; j < e; j++) { const int d = g.adj[j]; if (target[d] == r && pos[d] < i && pos[d] >= 0) need++; }
-        if (need) {
-            bool ok = false;
-            for (int s = 0; s < PB_SPIN; s++) if (ld_volatile(cnt + r) >= need) { ok = true; break; }
-            if (!ok) return false;
-            fence();
-        }
         float acc = initv ? initv[r] : 1.0f;
         int last = -1;
-        for (int k = 0; k < need; k++) {     // donors in position order (repeated-min: degree is tiny)
+        for (;;) {     // donors in position order (repeated-min: degree is tiny); each donor's word is polled directly
             int bp = 0x7fffffff, bd = -1;
             for (int j = b; j < e; j++) {
                 const int d = g.adj[j];
                 const int p = pos[d];
                 if (target[d] == r && p >= 0 && p < i && p > last && p < bp) { bp = p; bd = d; }
             }
-            acc = (float)((double)acc + (double)ld_cg(contrib + bd));
+            if (bd < 0) break;
+            unsigned long long w = 0;
+            bool ok = false;
+            for (int s = 0; s < PB_SPIN; s++) { w = ld_word(contrib + bd); if (word_seq(w)) { ok = true; break; } }
+            if (!ok) return false;
+            acc = (float)((double)acc + (double)word_value(w));
             last = bp;
         }
-        st_cg(contrib + r, acc);
-        const int t = target[r];
-        if (t >= 0 && !isOcean[t] && pos[t] > i) { fence(); atomic_add(cnt + t, 1); }
+        st_word(contrib + r, make_word(acc, 1));
         return true;
     }
 };
 // final value: init + every donor's contribution in position order; also the donor count (mod 256)
 struct AccumulateFinalK {
     Csr g; const int* pos; const int* target; const uint8_t* isOcean; const float* initv;
-    const float* contrib; float* flow; uint8_t* nUp;
+    const unsigned long long* contrib; float* flow; uint8_t* nUp;
     PB_DEV void operator()(int r) const {
         if (isOcean[r]) { flow[r] = initv ? initv[r] : 0.0f; if (nUp) nUp[r] = 0; return; }
         const int b = g.off[r], e = g.off[r + 1];
@@ -105,7 +100,7 @@ struct AccumulateFinalK {
                 if (target[d] == r && p >= 0 && p > last && p < bp) { bp = p; bd = d; }
             }
             if (bd < 0) break;
-            acc = (float)((double)acc + (double)contrib[bd]);
+            acc = (float)((double)acc + (double)word_value(contrib[bd]));
             last = bp; n++;
         }
         flow[r] = acc;
@@ -172,9 +167,15 @@ struct SolvePrepK {
     }
 };
 
+// The elevation of every land cell travels in a 64-bit (elevation, sequence) word: sequence = number of
+// operations of the cell's chain already applied.  An operation polls the words of the cells it touches
+// until each carries its own chain index, which hands it the current elevations in the same loads — no
+// fences, no separate counters (a naturally aligned 64-bit access is single-copy atomic).
+struct PackElevK { const float* elev; unsigned long long* ec; PB_DEV void operator()(int r) const { ec[r] = make_word(elev[r], 0); } };
+struct UnpackElevK { const unsigned long long* ec; const uint8_t* isOcean; float* elev; PB_DEV void operator()(int r) const { if (!isOcean[r]) elev[r] = word_value(ec[r]); } };
 struct SolveK {
     const int* order; int landCount; const int* target; const uint8_t* isOcean;
-    const float* cellDist; const float* flow; float* elev; int* cnt; const int* k0; const int* k1; const int* k2;
+    const float* cellDist; const float* flow; const float* elev; unsigned long long* ec; const int* k0; const int* k1; const int* k2;
     double K, m, dt;
     PB_DEV bool try_run(int a) const {
         const int r = order[landCount - 1 - a];     // ascending elevation
@@ -183,17 +184,22 @@ struct SolveK {
         const int gg = tLand ? target[t] : -1;
         const bool gLand = gg >= 0 && !isOcean[gg] && gg != r;
         const int n0 = k0[r], n1 = tLand ? k1[r] : 0, n2 = gLand ? k2[r] : 0;
+        unsigned long long wr = 0, wt = 0, wg = 0;
         bool ok = false;
         for (int s = 0; s < PB_SPIN; s++) {
-            if (ld_volatile(cnt + r) >= n0 && (!tLand || ld_volatile(cnt + t) >= n1) &&
-                (!gLand || ld_volatile(cnt + gg) >= n2)) { ok = true; break; }
+            wr = ld_word(ec + r);
+            if (word_seq(wr) != n0) continue;
+            if (tLand) { wt = ld_word(ec + t); if (word_seq(wt) != n1) continue; }
+            if (gLand) { wg = ld_word(ec + gg); if (word_seq(wg) != n2) continue; }
+            ok = true;
+            break;
         }
         if (!ok) return false;
-        fence();
         const float cd = cellDist[r];
+        float er = word_value(wr), et = tLand ? word_value(wt) : 0.0f;
         if (t >= 0 && cd > 0) {
-            const double hr0 = ld_cg(elev + r);
-            const double ht = ld_cg(elev + t);
+            const double hr0 = er;
+            const double ht = tLand ? (double)et : (double)elev[t];        // ocean receivers never change
             const double factor = K * pb_pow((double)flow[r], m) * dt / (double)cd;
             const double hrec = ht > 0 ? ht : 0.0;                 // Math.max(h_t, 0)
             double hnew = (hr0 + factor * hrec) / (1 + factor);
@@ -202,18 +208,20 @@ struct SolveK {
             const double eroded = hr0 - hnew;
             if (eroded > 0 && tLand) {
                 double slope = 0;
-                if (gg >= 0 && cellDist[t] > 0) slope = fabs(ht - (double)ld_cg(elev + gg)) / (double)cellDist[t];
+                if (gg >= 0 && cellDist[t] > 0) {
+                    const double hg = gLand ? (double)word_value(wg) : (gg == r ? hr0 : (double)elev[gg]);
+                    slope = fabs(ht - hg) / (double)cellDist[t];
+                }
                 const double deposit = eroded * (0.5 / (1 + slope * 50));
                 float nt = (float)(ht + deposit);
                 if ((double)nt > hnew) nt = (float)hnew;
-                st_cg(elev + t, nt);
+                et = nt;
             }
-            st_cg(elev + r, (float)hnew);
+            er = (float)hnew;
         }
-        fence();
-        atomic_add(cnt + r, 1);
-        if (tLand) atomic_add(cnt + t, 1);
-        if (gLand) atomic_add(cnt + gg, 1);
+        if (tLand) st_word(ec + t, make_word(et, n1 + 1));
+        if (gLand) st_word(ec + gg, make_word(word_value(wg), n2 + 1));
+        st_word(ec + r, make_word(er, n0 + 1));
         return true;
     }
 };

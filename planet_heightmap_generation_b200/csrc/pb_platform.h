@@ -136,6 +136,12 @@ PB_DEV float ld_cg(const float* p) { return __ldcg(p); }
 PB_DEV int ld_cg(const int* p) { return __ldcg(p); }
 PB_DEV void st_cg(float* p, float v) { __stcg(p, v); }
 PB_DEV void st_cg(int* p, int v) { __stcg(p, v); }
+// 64-bit (value, sequence) words: one naturally aligned access carries both, so a consumer that polls
+// the word needs no fence to pair the value with its sequence number
+PB_DEV unsigned long long ld_word(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+PB_DEV void st_word(unsigned long long* p, unsigned long long v) { __stcg(p, v); }
+PB_DEV float word_value(unsigned long long w) { return __uint_as_float((unsigned)(w & 0xffffffffull)); }
+PB_DEV unsigned long long make_word(float v, int seq) { return ((unsigned long long)(unsigned)seq << 32) | __float_as_uint(v); }
 #else
 PB_DEV int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 PB_DEV unsigned long long atomic_max64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
@@ -148,7 +154,12 @@ PB_DEV float ld_cg(const float* p) { return *p; }
 PB_DEV int ld_cg(const int* p) { return *p; }
 PB_DEV void st_cg(float* p, float v) { *p = v; }
 PB_DEV void st_cg(int* p, int v) { *p = v; }
+PB_DEV unsigned long long ld_word(const unsigned long long* p) { return *p; }
+PB_DEV void st_word(unsigned long long* p, unsigned long long v) { *p = v; }
+PB_DEV float word_value(unsigned long long w) { unsigned u = (unsigned)(w & 0xffffffffull); float f; memcpy(&f, &u, 4); return f; }
+PB_DEV unsigned long long make_word(float v, int seq) { unsigned u; memcpy(&u, &v, 4); return ((unsigned long long)(unsigned)seq << 32) | u; }
 #endif
+PB_DEV int word_seq(unsigned long long w) { return (int)(w >> 32); }
 
 // ---------------------------------------------------------------------------------------------
 // launches
