@@ -113,6 +113,7 @@ struct Mesh {
         if (n <= 0) throw Error("numRegions must be positive");
         if (hOff[0] != 0) throw Error("adjOffset[0] must be 0");
         for (int r = 0; r < n; r++) if (hOff[r + 1] < hOff[r]) throw Error("adjOffset must be non-decreasing");
+        for (int r = 0; r < n; r++) if (hOff[r + 1] - hOff[r] > 32) throw Error("cell degree above 32 is not supported");
         E = hOff[n];
         for (long long i = 0; i < E; i++) if (hAdj[i] < 0 || hAdj[i] >= n) throw Error("adjList entry out of range");
         hOffCopy.assign(hOff, hOff + n + 1); hAdjCopy.assign(hAdj, hAdj + E); hXyzCopy.assign(hXyz, hXyz + 3 * (size_t)n);

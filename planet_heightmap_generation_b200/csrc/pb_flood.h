@@ -386,24 +386,70 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeapEntry* sh = (HeapEntry*)smem_raw;                                  // [cap + 2]
     __shared__ volatile int done;
+    // mailbox between the heap warp and the expansion warp
+    __shared__ volatile int reqSeq, reqCell, respSeq, respCount;
+    __shared__ volatile uint32_t respKey[32];
+    __shared__ volatile int respCell[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.g.N;
     const unsigned FULL = 0xffffffffu;
-    if (tid == 0) done = 0;
+    if (tid == 0) { done = 0; reqSeq = 0; respSeq = 0; respCount = 0; }
     for (int w = tid; w < 64; w += blockDim.x) sh[w].c = 0;                  // helpers may peek before the first push
     __syncthreads();
 
-    if (warp != 0) {
-        // ---- prefetch helper: keep the rows of the heap's top entries hot in L1 -------------------
-        const int nHelpers = (blockDim.x >> 5) - 1;
+    if (warp == 1) {
+        // ---- expansion warp: lane j owns neighbour j of the cell the heap warp is popping.  It reads the
+        // CSR row, the visited flags, elevations and noise, decides fill / no fill, writes surface, drainTo
+        // and visited, and hands the new (key, cell) pairs back in adjacency order.  All of this overlaps
+        // the heap warp's sift-down.
+        for (int t = 1;; t++) {
+            while (reqSeq != t) { if (done) return; }
+            const int r = reqCell;
+            const int b = __ldg(a.g.off + r), e = __ldg(a.g.off + r + 1);
+            const double surfR = (double)__ldcg(a.surface + r);
+            uint32_t kbits = 0; int nb = -1; bool fresh = false;
+            if (b + lane < e) {
+                nb = __ldg(a.g.adj + b + lane);
+                const bool v = __ldcg(a.visited + nb) != 0;
+                const float el = __ldg(a.elev + nb);
+                const float k0 = __ldg(a.key0 + nb);
+                const double noise = __ldg(a.noise + nb);
+                if (!v) {
+                    fresh = true;
+                    float kf = k0;
+                    if ((double)el < surfR + PB_FLOOD_EPS) {
+                        const float s = (float)(surfR + PB_FLOOD_EPS);
+                        __stcg(a.surface + nb, s);
+                        kf = (float)((double)s + noise);
+                    }
+                    kbits = __float_as_uint(kf);
+                    __stcg(a.drainTo + nb, r);
+                    __stcg(a.visited + nb, (uint8_t)1);
+                }
+            }
+            const unsigned m = __ballot_sync(FULL, fresh);
+            if (fresh) { const int slot = __popc(m & ((1u << lane) - 1)); respKey[slot] = kbits; respCell[slot] = nb; }
+            if (lane == 0) respCount = __popc(m);
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) respSeq = t;
+        }
+    }
+    if (warp > 1) {
+        // ---- prefetch helpers: keep the rows of the heap's top entries hot in L1 -------------------
+        const int nHelpers = (blockDim.x >> 5) - 2;
         while (!done) {
-            for (int idx = warp - 1; idx < 15; idx += nHelpers) {
+            for (int idx = warp - 2; idx < 15; idx += nHelpers) {
                 int c = ((volatile HeapEntry*)sh)[idx + 1].c;
                 if (c < 0 || c >= N) continue;
                 const int b = __ldg(a.g.off + c), e = __ldg(a.g.off + c + 1);
                 if (lane < e - b && e - b <= 32) {
                     const int nb = __ldg(a.g.adj + b + lane);
-                    if (nb >= 0 && nb < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
+                    if (nb >= 0 && nb < N) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.elev + nb));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.key0 + nb));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.noise + nb));
+                    }
                 }
             }
             __nanosleep(100);
@@ -446,15 +492,10 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         push(__float_as_uint(__ldg(a.key0 + c)), c);
     }
     __syncwarp();
-    int r = n > 0 ? sh[1].c : -1;
-    int b = 0, e = 0;
-    float surfRf = 0.f;
-    if (r >= 0) { b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r); }
-    while (n > 0) {
+    for (int t = 1; n > 0; t++) {
         if (n > maxN) maxN = n;
-        // neighbour ids of the popped cell: in flight while the sift-down runs
-        int nb = -1;
-        if (b + lane < e) nb = __ldg(a.g.adj + b + lane);
+        // hand the popped cell to the expansion warp, then restore the heap while it works
+        if (lane == 0) { reqCell = sh[1].c; __threadfence_block(); reqSeq = t; }
         // pop: MinHeap.pop (:27-46) — last → root, sift down along the min-child path (left child on ties)
         --n;
         const HeapEntry last = n < cap ? sh[n + 1] : H.ld(n);
@@ -490,41 +531,12 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
             if (i < cap) sh[i + 1] = last; else H.st(i, last);
         }
         __syncwarp();
-        // expand r: lane j owns neighbour j; visited flag and elevation are fetched together
-        const double surfR = (double)surfRf;
-        uint32_t kbits = 0; bool fresh = false;
-        if (nb >= 0) {
-            const bool v = __ldcg(a.visited + nb) != 0;
-            const float el = __ldg(a.elev + nb);
-            const float k0 = __ldg(a.key0 + nb);
-            const double noise = __ldg(a.noise + nb);
-            if (!v) {
-                fresh = true;
-                float kf = k0;
-                if ((double)el < surfR + PB_FLOOD_EPS) {
-                    const float s = (float)(surfR + PB_FLOOD_EPS);
-                    __stcg(a.surface + nb, s);
-                    kf = (float)((double)s + noise);
-                }
-                kbits = __float_as_uint(kf);
-                __stcg(a.drainTo + nb, r);
-                __stcg(a.visited + nb, (uint8_t)1);
-            }
-        }
-        unsigned m = __ballot_sync(FULL, fresh);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t kk = __shfl_sync(FULL, kbits, src);
-            const int cc = __shfl_sync(FULL, nb, src);
-            push(kk, cc);
-        }
+        // push the cells the expansion warp discovered, in adjacency order
+        while (respSeq != t) {}
+        __threadfence_block();
+        const int cnt = respCount;
+        for (int k = 0; k < cnt; k++) push(respKey[k], respCell[k]);
         __syncwarp();
-        // next pop is the root now; start its row / surface loads right away
-        if (n > 0) {
-            r = sh[1].c;
-            b = __ldg(a.g.off + r); e = __ldg(a.g.off + r + 1); surfRf = __ldcg(a.surface + r);
-        }
     }
     if (lane == 0) { done = 1; a.status[0] = maxN; }
 }

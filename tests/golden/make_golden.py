@@ -1,0 +1,60 @@
+"""Regenerates tests/golden/oracle_checksums.json: SHA-256 of every oracle output on a 3 000-cell seeded planet.
+
+The reference has no golden vectors and cannot run here (no JS runtime), so these pins do not prove parity with
+the reference; they freeze the oracle's behaviour so that an accidental change to oracle/ (or to pb_detmath.h)
+is caught by `pytest -m "not gpu"`.  Run:  python tests/golden/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+SLIDERS = dict(smoothing=0.10, glacialErosion=0.50, hydraulicErosion=0.50, thermalErosion=0.10, ridgeSharpening=0.50,
+               terrainWarp=0.75)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def compute():
+    from oracle import binding as oracle
+    from planet_heightmap_generation_b200.mesh import build_sphere_from_points
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plate_tables
+    xyz = oracle.fibonacci_sphere(3000, 0.75, 42)
+    mesh, xyz = build_sphere_from_points(xyz)
+    out = {"r_xyz": sha(xyz), "adjOffset": sha(mesh.adjOffset), "adjList": sha(mesh.adjList)}
+    nd = oracle.neighbor_dist(mesh, xyz)
+    out["neighborDist"] = sha(nd)
+    r_plate, plates, seeds, r_super, sp = synthetic_plate_tables(xyz, synthetic_elevation(xyz, 42, 0.3), 42)
+    out["r_plate"] = sha(r_plate)
+    oe = oracle.Elevation(mesh, xyz)
+    oe.assign(r_plate, plates, seeds, 42, 0.4, 42, 5, r_super, sp)
+    elev = oe.get("r_elevation")
+    for k in ("r_elevation", "r_stress", "dist_mountain", "dist_ocean", "dist_coastline", "dist_coast", "dist_coast_land",
+              "dBdry", "backArcDist", "hotspot", "coastal", "noise", "tectonic"):
+        out["elevation." + k] = sha(oe.get(k))
+    delta, ocean = oracle.run_post_processing(mesh, xyz, elev, SLIDERS, nd, 42, oe.get("hotspot"))
+    out["post.r_elevation"] = sha(elev)
+    out["post.erosionDelta"] = sha(delta)
+    out["post.r_isOcean"] = sha(ocean)
+    pio = {p for p, v in plates.items() if v["isOcean"]}
+    oc = oracle.Climate(mesh, xyz)
+    out["climate.r_koppen"] = sha(oc.run_all(elev, pio, r_plate, 42))
+    for k in ("r_continentality", "r_pressure_summer", "r_wind_east_winter", "r_wind_speed_summer", "itczLatsSummer",
+              "r_ocean_warmth_summer", "r_ocean_speed_winter", "r_precip_summer", "r_precip_winter", "r_rainshadow_summer",
+              "r_temperature_summer", "r_temperature_winter"):
+        out["climate." + k] = sha(oc.get(k))
+    out["climate.r_coastDistLand"] = sha(oc.get("r_coastDistLand", np.int32))
+    return out
+
+
+if __name__ == "__main__":
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_checksums.json")
+    json.dump(compute(), open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path)
