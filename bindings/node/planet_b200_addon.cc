@@ -1,0 +1,253 @@
+// planet_b200_addon.cc — Node-API addon over include/planet_b200.h.
+//
+// Exposes the reference's stage functions (same names, same argument order, typed arrays in place) so that
+// js/planet-worker.js can import them from this addon instead of the ES modules js/terrain-post.js,
+// js/elevation.js, js/wind.js, js/ocean.js, js/precipitation.js, js/temperature.js, js/koppen.js
+// (see bindings/node/planet_worker_shim.mjs and INTEGRATION.md).  The worker keeps exactly one mesh at a time
+// (its retained state W, js/planet-worker.js:277-292); so does this addon.
+//
+// Not buildable in this image (no Node headers); type-checked against bindings/node/stub/node_api.h.
+// Build with node-gyp:  sources: [planet_b200_addon.cc], include_dirs: [../../include],
+//                        libraries: [-lplanet_b200], cflags_cc: [-std=c++17].
+#include <node_api.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "planet_b200.h"
+
+namespace {
+
+pb_context* g_ctx = nullptr;
+pb_mesh* g_mesh = nullptr;
+pb_climate* g_clim = nullptr;
+
+#define PB_TRY(env, expr)                                                     \
+    do { if ((expr) != PB_OK) { napi_throw_error(env, nullptr, pb_last_error()); return nullptr; } } while (0)
+#define NEED_MESH(env)                                                        \
+    do { if (!g_mesh) { napi_throw_error(env, nullptr, "setMesh() has not been called"); return nullptr; } } while (0)
+
+struct Args {
+    napi_env env; size_t argc = 16; napi_value v[16];
+    Args(napi_env e, napi_callback_info info) : env(e) { napi_get_cb_info(e, info, &argc, v, nullptr, nullptr); }
+    bool present(size_t i) const {
+        if (i >= argc) return false;
+        napi_valuetype t; napi_typeof(env, v[i], &t);
+        return t != napi_undefined && t != napi_null;
+    }
+    double num(size_t i, double dflt = 0) const { double d = dflt; if (present(i)) napi_get_value_double(env, v[i], &d); return d; }
+    int32_t i32(size_t i, int32_t dflt = 0) const { int32_t d = dflt; if (present(i)) napi_get_value_int32(env, v[i], &d); return d; }
+    template <class T> T* typed(size_t i, size_t* len = nullptr) const {
+        if (!present(i)) return nullptr;
+        napi_typedarray_type t; size_t n; void* data; napi_value buf; size_t off;
+        if (napi_get_typedarray_info(env, v[i], &t, &n, &data, &buf, &off) != napi_ok) return nullptr;
+        if (len) *len = n;
+        return static_cast<T*>(data);
+    }
+};
+
+double prop_num(napi_env env, napi_value obj, const char* name, double dflt = 0) {
+    bool has = false; napi_has_named_property(env, obj, name, &has);
+    if (!has) return dflt;
+    napi_value v; napi_get_named_property(env, obj, name, &v);
+    double d = dflt; napi_get_value_double(env, v, &d);
+    return d;
+}
+
+napi_value new_typed(napi_env env, napi_typedarray_type type, size_t n, size_t elem, void** data) {
+    napi_value ab, ta;
+    napi_create_arraybuffer(env, n * elem, data, &ab);
+    napi_create_typedarray(env, type, n, ab, 0, &ta);
+    return ta;
+}
+napi_value undefined(napi_env env) { napi_value u; napi_get_undefined(env, &u); return u; }
+
+// setMesh(numRegions, adjOffset:Int32Array, adjList:Int32Array, r_xyz:Float32Array)   after buildSphere (:149)
+napi_value SetMesh(napi_env env, napi_callback_info info) {
+    Args a(env, info);
+    if (!g_ctx) PB_TRY(env, pb_context_create(0, &g_ctx));
+    if (g_clim) { pb_climate_destroy(g_clim); g_clim = nullptr; }
+    if (g_mesh) { pb_mesh_destroy(g_mesh); g_mesh = nullptr; }
+    PB_TRY(env, pb_mesh_create(g_ctx, a.i32(0), a.typed<int32_t>(1), a.typed<int32_t>(2), a.typed<float>(3), &g_mesh));
+    PB_TRY(env, pb_climate_create(g_mesh, &g_clim));
+    return undefined(env);
+}
+// setOption(name, value)
+napi_value SetOption(napi_env env, napi_callback_info info) {
+    Args a(env, info);
+    char name[64] = {0}, value[64] = {0}; size_t n;
+    napi_get_value_string_utf8(env, a.v[0], name, sizeof name, &n);
+    napi_get_value_string_utf8(env, a.v[1], value, sizeof value, &n);
+    if (!g_ctx) PB_TRY(env, pb_context_create(0, &g_ctx));
+    PB_TRY(env, pb_set_option(g_ctx, name, value));
+    return undefined(env);
+}
+// computeNeighborDist(mesh, r_xyz) → Float32Array                                   js/sphere-mesh.js:191
+napi_value ComputeNeighborDist(napi_env env, napi_callback_info info) {
+    NEED_MESH(env);
+    void* data; napi_value out = new_typed(env, napi_float32_array, (size_t)pb_mesh_num_edges(g_mesh), 4, &data);
+    PB_TRY(env, pb_compute_neighbor_dist(g_mesh, static_cast<float*>(data)));
+    return out;
+}
+// warpTerrain(mesh, r_elevation, r_xyz, seed, strength, r_hotspot)                  js/terrain-post.js:233
+napi_value WarpTerrain(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_warp_terrain(g_mesh, a.typed<float>(1), a.num(3), a.num(4), a.typed<float>(5)));
+    return undefined(env);
+}
+// smoothElevation(mesh, r_elevation, r_isOcean, iterations, strength)               :317
+napi_value SmoothElevation(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_smooth_elevation(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    return undefined(env);
+}
+// erodeComposite(mesh, r_elevation, r_xyz, r_isOcean, hIters, K, m, dt, tIters, talusSlope, kThermal, gIters,
+//                glacialStrength, neighborDist)                                      :369
+napi_value ErodeComposite(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_erode_composite(g_mesh, a.typed<float>(1), a.typed<uint8_t>(3), a.i32(4), a.num(5), a.num(6), a.num(7), a.i32(8),
+                                   a.num(9), a.num(10), a.i32(11, 0), a.num(12, 0)));
+    return undefined(env);
+}
+// sharpenRidges / applySoilCreep(mesh, r_elevation, r_isOcean, iterations, strength) :713 / :758
+napi_value SharpenRidges(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_sharpen_ridges(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    return undefined(env);
+}
+napi_value ApplySoilCreep(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_apply_soil_creep(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    return undefined(env);
+}
+// runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot) → {dl_erosionDelta, postTiming}
+//                                                                                    js/planet-worker.js:40-102
+napi_value RunPostProcessing(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    pb_post_params p;
+    p.smoothing = prop_num(env, a.v[3], "smoothing"); p.glacialErosion = prop_num(env, a.v[3], "glacialErosion");
+    p.hydraulicErosion = prop_num(env, a.v[3], "hydraulicErosion"); p.thermalErosion = prop_num(env, a.v[3], "thermalErosion");
+    p.ridgeSharpening = prop_num(env, a.v[3], "ridgeSharpening"); p.terrainWarp = prop_num(env, a.v[3], "terrainWarp");
+    p.hItersOverride = (int32_t)prop_num(env, a.v[3], "hItersOverride", -1);
+    const size_t n = (size_t)pb_mesh_num_regions(g_mesh);
+    void* d; napi_value delta = new_typed(env, napi_float32_array, n, 4, &d);
+    PB_TRY(env, pb_run_post_processing(g_mesh, a.typed<float>(2), &p, a.num(5), a.typed<float>(6), static_cast<float*>(d), nullptr));
+    napi_value out; napi_create_object(env, &out);
+    napi_set_named_property(env, out, "dl_erosionDelta", delta);
+    double ms[5]; static const char* stage[5] = {"Terrain warp", "Smoothing", "Erosion composite", "Ridge sharpening", "Soil creep"};
+    if (pb_last_post_timing(g_mesh, ms) == PB_OK) {
+        napi_value t; napi_create_object(env, &t);
+        for (int k = 0; k < 5; k++) { napi_value v; napi_create_double(env, ms[k], &v); napi_set_named_property(env, t, stage[k], v); }
+        napi_set_named_property(env, out, "postTimingMs", t);
+    }
+    return out;
+}
+
+// plate table from parallel arrays: (ids:Int32Array, isOcean:Uint8Array, pole:Float64Array[3n], omega:Float64Array, density:Float64Array)
+bool plate_table(const Args& a, size_t first, pb_plate_table* t) {
+    size_t n = 0;
+    t->ids = a.typed<int32_t>(first, &n); t->n = (int32_t)n;
+    t->isOcean = a.typed<uint8_t>(first + 1); t->pole = a.typed<double>(first + 2);
+    t->omega = a.typed<double>(first + 3); t->density = a.typed<double>(first + 4);
+    return t->ids && t->isOcean && t->pole && t->omega && t->density;
+}
+// assignElevation(r_plate, plateIds, plateIsOcean, platePole, plateOmega, plateDensity, plateSeeds:Int32Array, noiseSeed,
+//                 noiseMag, seed, spread, [r_superPlate, sIds, sIsOcean, sPole, sOmega, sDensity])
+//   → {r_elevation, r_stress, mountain_r, coastline_r, ocean_r, debugLayers}         js/elevation.js:216
+// (the shim flattens plateVec / plateDensity / plateIsOcean / superPlateData into these arrays)
+napi_value AssignElevation(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    pb_plate_table P, SP;
+    if (!plate_table(a, 1, &P)) { napi_throw_error(env, nullptr, "bad plate table"); return nullptr; }
+    size_t nSeeds = 0; const int32_t* seeds = a.typed<int32_t>(6, &nSeeds);
+    const bool dual = a.present(11);
+    if (dual && !plate_table(a, 12, &SP)) { napi_throw_error(env, nullptr, "bad super-plate table"); return nullptr; }
+    const size_t n = (size_t)pb_mesh_num_regions(g_mesh);
+    pb_elevation_result r;
+    napi_value out, dbg; napi_create_object(env, &out); napi_create_object(env, &dbg);
+    void* d;
+    napi_set_named_property(env, out, "r_elevation", new_typed(env, napi_float32_array, n, 4, &d)); r.r_elevation = static_cast<float*>(d);
+    napi_set_named_property(env, out, "r_stress", new_typed(env, napi_float32_array, n, 4, &d)); r.r_stress = static_cast<float*>(d);
+    napi_set_named_property(env, out, "mountain_r", new_typed(env, napi_uint8_array, n, 1, &d)); r.mountain_r = static_cast<uint8_t*>(d);
+    napi_set_named_property(env, out, "coastline_r", new_typed(env, napi_uint8_array, n, 1, &d)); r.coastline_r = static_cast<uint8_t*>(d);
+    napi_set_named_property(env, out, "ocean_r", new_typed(env, napi_uint8_array, n, 1, &d)); r.ocean_r = static_cast<uint8_t*>(d);
+    static const char* layers[12] = {"base", "tectonic", "noise", "interior", "coastal", "ocean", "hotspot", "tecActivity", "margins",
+                                     "backArc", "foldRidge", "orogenicPower"};
+    for (int k = 0; k < 12; k++) { napi_set_named_property(env, dbg, layers[k], new_typed(env, napi_float32_array, n, 4, &d)); r.debug[k] = static_cast<float*>(d); }
+    napi_set_named_property(env, out, "debugLayers", dbg);
+    PB_TRY(env, pb_assign_elevation(g_mesh, &P, a.typed<int32_t>(0), seeds, (int32_t)nSeeds, a.num(7), a.num(8), a.num(9), a.num(10),
+                                    dual ? &SP : nullptr, dual ? a.typed<int32_t>(11) : nullptr, &r));
+    return out;
+}
+
+// climate stages: results stay on the device; getClimateField(name) fetches one array by the reference's key
+napi_value ComputeWind(napi_env env, napi_callback_info info) {          // (r_elevation, plateIsOceanIds:Int32Array, r_plate, noiseSeed, axialTilt)
+    NEED_MESH(env); Args a(env, info);
+    size_t nIds = 0; const int32_t* ids = a.typed<int32_t>(1, &nIds);
+    PB_TRY(env, pb_compute_wind(g_clim, a.typed<float>(0), ids, (int32_t)nIds, a.typed<int32_t>(2), a.num(3), a.num(4, 23.5)));
+    return undefined(env);
+}
+napi_value ComputeOceanCurrents(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_compute_ocean_currents(g_clim, a.typed<float>(0)));
+    return undefined(env);
+}
+napi_value ComputePrecipitation(napi_env env, napi_callback_info info) {  // (r_elevation, precipitationOffset, landCoverage)
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_compute_precipitation(g_clim, a.typed<float>(0), a.num(1, 0), a.num(2, 0.3)));
+    return undefined(env);
+}
+napi_value ComputeTemperature(napi_env env, napi_callback_info info) {    // (r_elevation, temperatureOffset)
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_compute_temperature(g_clim, a.typed<float>(0), a.num(1, 0)));
+    return undefined(env);
+}
+napi_value ClassifyKoppen(napi_env env, napi_callback_info info) {        // (r_elevation) → Uint8Array
+    NEED_MESH(env); Args a(env, info);
+    void* d; napi_value out = new_typed(env, napi_uint8_array, (size_t)pb_mesh_num_regions(g_mesh), 1, &d);
+    PB_TRY(env, pb_classify_koppen(g_clim, a.typed<float>(0), static_cast<uint8_t*>(d)));
+    return out;
+}
+napi_value GetClimateField(napi_env env, napi_callback_info info) {       // (name) → typed array
+    NEED_MESH(env); Args a(env, info);
+    char name[96] = {0}; size_t len;
+    napi_get_value_string_utf8(env, a.v[0], name, sizeof name, &len);
+    int32_t kind; int64_t count;
+    PB_TRY(env, pb_climate_field_info(g_clim, name, &kind, &count));
+    void* d;
+    napi_value out = new_typed(env, kind == 0 ? napi_float32_array : kind == 1 ? napi_int32_array : napi_uint8_array, (size_t)count,
+                               kind == 2 ? 1 : 4, &d);
+    PB_TRY(env, pb_climate_get(g_clim, name, d));
+    return out;
+}
+// smoothField(mesh, field, passes)                                                  js/climate-util.js:5
+napi_value SmoothField(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    PB_TRY(env, pb_smooth_field(g_mesh, a.typed<float>(1), a.i32(2)));
+    return undefined(env);
+}
+
+}  // namespace
+
+NAPI_MODULE_INIT() {
+    const napi_property_descriptor props[] = {
+        {"setMesh", nullptr, SetMesh, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"setOption", nullptr, SetOption, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeNeighborDist", nullptr, ComputeNeighborDist, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"warpTerrain", nullptr, WarpTerrain, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"smoothElevation", nullptr, SmoothElevation, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"erodeComposite", nullptr, ErodeComposite, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"sharpenRidges", nullptr, SharpenRidges, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"applySoilCreep", nullptr, ApplySoilCreep, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"runPostProcessing", nullptr, RunPostProcessing, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"assignElevationFlat", nullptr, AssignElevation, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeWindFlat", nullptr, ComputeWind, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeOceanCurrentsFlat", nullptr, ComputeOceanCurrents, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computePrecipitationFlat", nullptr, ComputePrecipitation, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeTemperatureFlat", nullptr, ComputeTemperature, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"classifyKoppenFlat", nullptr, ClassifyKoppen, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"getClimateField", nullptr, GetClimateField, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"smoothField", nullptr, SmoothField, nullptr, nullptr, nullptr, napi_default, nullptr},
+    };
+    napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
+    return exports;
+}

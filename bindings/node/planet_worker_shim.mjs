@@ -1,0 +1,87 @@
+// planet_worker_shim.mjs — the reference's stage functions (same names, same signatures, same result keys)
+// implemented over the N-API addon.  js/planet-worker.js keeps its handlers unchanged and only swaps its imports:
+//
+//   - import { warpTerrain, smoothElevation, erodeComposite, sharpenRidges, applySoilCreep } from './terrain-post.js';
+//   - import { assignElevation } from './elevation.js';
+//   - import { computeWind } from './wind.js';  import { computeOceanCurrents } from './ocean.js';  …
+//   + import * as gpu from '../bindings/node/planet_worker_shim.mjs';   // then gpu.setMesh(mesh, r_xyz) after buildSphere (:149)
+//
+// (Node worker_threads build of the worker; the browser build keeps the JS modules.)  Not runnable in this image.
+import { createRequire } from 'node:module';
+const native = createRequire(import.meta.url)('./build/Release/planet_b200_addon.node');
+
+export function setMesh(mesh, r_xyz) { native.setMesh(mesh.numRegions, mesh.adjOffset, mesh.adjList, r_xyz); }
+export const setOption = native.setOption;
+export const computeNeighborDist = native.computeNeighborDist;      // (mesh, r_xyz) → Float32Array
+export const warpTerrain = native.warpTerrain;                      // in place, like the reference
+export const smoothElevation = native.smoothElevation;
+export const erodeComposite = native.erodeComposite;
+export const sharpenRidges = native.sharpenRidges;
+export const applySoilCreep = native.applySoilCreep;
+export const smoothField = native.smoothField;
+
+// runPostProcessing is module-private in planet-worker.js (:40-102); the worker may call this instead.
+export function runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot) {
+  const r = native.runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot ?? null);
+  return { dl_erosionDelta: r.dl_erosionDelta,
+           postTiming: Object.entries(r.postTimingMs ?? {}).map(([stage, ms]) => ({ stage, ms })) };
+}
+
+function flattenPlates(isOceanSet, vec, density, order) {
+  const ids = Int32Array.from(order ?? Object.keys(vec).map(Number));
+  const n = ids.length;
+  const isOcean = new Uint8Array(n), pole = new Float64Array(3 * n), omega = new Float64Array(n), dens = new Float64Array(n);
+  ids.forEach((pid, k) => {
+    isOcean[k] = isOceanSet.has(pid) ? 1 : 0;
+    pole.set(vec[pid].pole, 3 * k); omega[k] = vec[pid].omega; dens[k] = density[pid];
+  });
+  return [ids, isOcean, pole, omega, dens];
+}
+
+// assignElevation(mesh, r_xyz, plateIsOcean, r_plate, plateVec, plateSeeds, noise, noiseMag, seed, spread, plateDensity, superPlateData)
+// `noise` must expose the seed it was built from (new SimplexNoise(seed), js/planet-worker.js:203): pass {seed}.
+export function assignElevation(mesh, r_xyz, plateIsOcean, r_plate, plateVec, plateSeeds, noise, noiseMag, seed, spread,
+                                plateDensity, superPlateData) {
+  const args = [r_plate, ...flattenPlates(plateIsOcean, plateVec, plateDensity), Int32Array.from(plateSeeds),
+                noise.seed, noiseMag, seed, spread];
+  if (superPlateData) {
+    args.push(superPlateData.r_superPlate,
+              ...flattenPlates(superPlateData.superPlateIsOcean, superPlateData.superPlateVec, superPlateData.superPlateDensity));
+  }
+  const r = native.assignElevationFlat(...args);
+  const toSet = (mask) => { const s = new Set(); for (let i = 0; i < mask.length; i++) if (mask[i]) s.add(i); return s; };
+  if (superPlateData) r.debugLayers.superPlates = new Float32Array(superPlateData.r_superPlate);
+  // the reference returns insertion-ordered Sets; downstream code only tests membership / draws the regions
+  return { r_elevation: r.r_elevation, mountain_r: toSet(r.mountain_r), coastline_r: toSet(r.coastline_r),
+           ocean_r: toSet(r.ocean_r), r_stress: r.r_stress, debugLayers: r.debugLayers, _timing: [] };
+}
+
+// result objects fetch their arrays from the device on first access
+function lazyResult(keys, extra = {}) {
+  const cache = { ...extra };
+  return new Proxy(cache, { get: (t, k) => (k in t ? t[k] : (keys.includes(k) ? (t[k] = native.getClimateField(k)) : undefined)),
+                            has: (t, k) => k in t || keys.includes(k), ownKeys: () => [...new Set([...Object.keys(cache), ...keys])] });
+}
+const S = ['summer', 'winter'];
+const WIND_KEYS = [...S.flatMap(s => [`r_pressure_${s}`, `r_wind_east_${s}`, `r_wind_north_${s}`, `r_wind_speed_${s}`]),
+  'itczLons', 'itczLatsSummer', 'itczLatsWinter', 'r_lat', 'r_lon', 'r_sinLat', 'r_isLand', 'r_continentality', 'r_coastDistLand',
+  'r_plateContinentality', 'r_eastX', 'r_eastY', 'r_eastZ', 'r_northX', 'r_northY', 'r_northZ'];
+const OCEAN_KEYS = S.flatMap(s => [`r_ocean_current_east_${s}`, `r_ocean_current_north_${s}`, `r_ocean_speed_${s}`, `r_ocean_warmth_${s}`]);
+
+export function computeWind(mesh, r_xyz, r_elevation, plateIsOcean, r_plate, noise, axialTilt = 23.5) {
+  native.computeWindFlat(r_elevation, Int32Array.from(plateIsOcean), r_plate, noise.seed, axialTilt);
+  return lazyResult(WIND_KEYS, { _windTiming: [] });
+}
+export function computeOceanCurrents(mesh, r_xyz, r_elevation, windResult) {
+  native.computeOceanCurrentsFlat(r_elevation);
+  return lazyResult(OCEAN_KEYS, { _oceanTiming: [] });
+}
+export function computePrecipitation(mesh, r_xyz, r_elevation, windResult, oceanResult, precipitationOffset = 0, landCoverage = 0.3) {
+  native.computePrecipitationFlat(r_elevation, precipitationOffset, landCoverage);
+  return lazyResult(S.flatMap(s => [`r_precip_${s}`, `r_rainshadow_${s}`]), { _precipTiming: [] });
+}
+export function computeTemperature(mesh, r_xyz, r_elevation, windResult, oceanResult, precipResult, temperatureOffset = 0) {
+  native.computeTemperatureFlat(r_elevation, temperatureOffset);
+  return lazyResult(S.map(s => `r_temperature_${s}`), { _tempTiming: [] });
+}
+export function classifyKoppen(mesh, r_elevation, tempResult, precipResult) { return native.classifyKoppenFlat(r_elevation); }

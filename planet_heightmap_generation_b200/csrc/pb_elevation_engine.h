@@ -10,6 +10,7 @@
 //           payloads (A.8), the p97 stress normaliser and the ≤ 35 RNG-placed hotspot domes.
 // The host part is the engine's own code (not the oracle) and is what SURVEY lists as "host-serial".
 #pragma once
+#include <chrono>
 #include <thread>
 #include <unordered_map>
 #include "pb_engine.h"
@@ -144,6 +145,15 @@ struct Elevation {
                 const int* r_super, const ElevationOutputs& out) {
         const Exec& x = ex();
         const int* off = m->hOffCopy.data(); const int* adj = m->hAdjCopy.data();
+        const bool dbgT = getenv("PB_DEBUG") != nullptr;
+        auto tNow = [] { return std::chrono::steady_clock::now(); };
+        auto t0 = tNow();
+        auto lap = [&](const char* what) {
+            if (!dbgT) return;
+            auto t1 = tNow();
+            fprintf(stderr, "[pb] elevation %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        };
         // noise tables: main, rift(+419), fold(+557), coast(+77,+133,+211), arc(+307), hotspot(+501,+502,+503)
         const double seeds10[10] = {noiseSeed, seed + 419, seed + 557, seed + 77, seed + 133, seed + 211, seed + 307, seed + 501, seed + 502, seed + 503};
         noiseTabs.ensure(10 * 1024);
@@ -162,6 +172,7 @@ struct Elevation {
         const bool dual = SP != nullptr;
         if (dual) { const PlateTab tS = dSP.upload(*SP, x.stream); run_collisions(1, tS, r_super_dev, NZ(0), super); }
         stream_sync(x.stream);
+        lap("collisions (device) + d2h");
 
         // 2. blend (:250-327)
         OrderedCells mountain, coastline, ocean;
@@ -198,6 +209,7 @@ struct Elevation {
             }
         }
 
+        lap("sets + blend");
         // 3. stress propagation (:329-362)
         const double scaleFactor = sqrt(N / 10000.0);
         const double baseDecay = 0.5 + spread * 0.04;
@@ -217,6 +229,7 @@ struct Elevation {
             }
         }
 
+        lap("propagateStress");
         // 4. plate representatives, seed sets (:368-388)
         {
             std::unordered_map<int, int> plateRep;
@@ -243,6 +256,7 @@ struct Elevation {
             for (int j = off[r], e = off[r + 1]; j < e; j++) if (isOcean[adj[j]]) { coastSeeds.add(adj[j]); landCoastSeeds.push_back(r); break; }
         }
 
+        lap("representatives + seeds");
         // 5. five randomized fills, concurrently (:392-426)
         std::vector<float> hd[5];
         {
@@ -255,6 +269,7 @@ struct Elevation {
             for (auto& t : th) t.join();
         }
 
+        lap("5 distance fills (threads)");
         // 6. maxStress = p97 of the non-trivial stresses (:443-453)
         double maxStress = 0;
         {
@@ -327,10 +342,12 @@ struct Elevation {
             t1.join(); t2.join(); t3.join(); t4.join();
         }
 
+        lap("p97 + capped BFS (threads)");
         // 8. hotspot domes (:1148-1262)
         std::vector<DomeDev> domes;
         build_domes(P, r_plate, seed, domes);
 
+        lap("hotspot domes");
         // 9. upload, device synthesis
         auto up = [&](DevBuf<float>& b, const std::vector<float>& h) { dev_copy(b.ensure(N), h.data(), sizeof(float) * (size_t)N, 0, x.stream); return b.p; };
         auto up8 = [&](DevBuf<uint8_t>& b, const std::vector<uint8_t>& h) { dev_copy(b.ensure(N), h.data(), (size_t)N, 0, x.stream); return b.p; };
@@ -364,6 +381,7 @@ struct Elevation {
         x.for_each(N, HotspotK{m->xyz.p, domesD.p, (int)domes.size(), NZ(7), NZ(8), out.elev, out.dbg.hotspot});
         x.for_each(N, CompressPeaksK{out.elev});
         stream_sync(x.stream);      // host vectors above are the sources of the async uploads
+        lap("h2d + synthesis kernels");
     }
 
     // hotspot dome list :1130-1262 (host: ≤ 5 plumes × chain, Park–Miller driven)

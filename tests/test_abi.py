@@ -45,3 +45,17 @@ def test_context_create_fails_loudly_without_gpu():
     ctx = ctypes.c_void_p()
     assert lib.dll.pb_context_create(0, ctypes.byref(ctx)) != 0
     assert b"CUDA" in lib.dll.pb_last_error() or b"cuda" in lib.dll.pb_last_error()
+
+
+def test_node_addon_type_checks_against_the_header():
+    """bindings/node/planet_b200_addon.cc (the N-API shim a maintainer builds with node-gyp) must stay in sync with
+    include/planet_b200.h; no Node toolchain exists here, so it is type-checked against a stub <node_api.h>."""
+    import subprocess
+    src = os.path.join(ROOT, "bindings", "node", "planet_b200_addon.cc")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "bindings", "node", "stub"),
+                           "-I" + os.path.join(ROOT, "include"), src])
+    text = open(src).read()
+    for fn in ("pb_warp_terrain", "pb_smooth_elevation", "pb_erode_composite", "pb_sharpen_ridges", "pb_apply_soil_creep",
+               "pb_run_post_processing", "pb_assign_elevation", "pb_compute_wind", "pb_compute_ocean_currents",
+               "pb_compute_precipitation", "pb_compute_temperature", "pb_classify_koppen", "pb_climate_get"):
+        assert fn in text, fn
