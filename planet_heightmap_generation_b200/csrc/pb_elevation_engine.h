@@ -114,10 +114,13 @@ struct Elevation {
             frontier.swap(next);
         }
     }
-    struct ParkMillerInt {   // makeRandInt (js/rng.js:8-11)
-        ParkMiller rng;
-        explicit ParkMillerInt(double seed) : rng(seed) {}
-        long long operator()(double n) { return (long long)floor(rng.next() * n); }
+    struct ParkMillerInt {   // makeRandInt (js/rng.js:8-11); the state is an integer < 2^31, so the JS double
+        unsigned long long s;  // arithmetic (s*16807) % 2147483647 is reproduced exactly in 64-bit integers
+        explicit ParkMillerInt(double seed) { s = (unsigned long long)(fmod(fabs(floor(seed * 9301.0 + 49297.0)), 2147483646.0) + 1.0); }
+        long long operator()(double n) {
+            s = (s * 16807ull) % 2147483647ull;
+            return (long long)floor(((double)(s - 1) / 2147483646.0) * n);
+        }
     };
     static void distance_field(const int* off, const int* adj, int N, const std::vector<int>& seeds, const uint8_t* isStop, double seed,
                                std::vector<float>& dist) {   // :164-189
@@ -257,19 +260,16 @@ struct Elevation {
         }
 
         lap("representatives + seeds");
-        // 5. five randomized fills, concurrently (:392-426)
+        // 5. five randomized fills (:392-426), each on its own thread; they run concurrently with the capped BFS below
         std::vector<float> hd[5];
-        {
-            std::thread th[4];
-            th[0] = std::thread([&] { distance_field(off, adj, N, stressMountain, ocean.in.data(), seed + 1, hd[0]); });
-            th[1] = std::thread([&] { distance_field(off, adj, N, ocean.items, coastline.in.data(), seed + 2, hd[1]); });
-            th[2] = std::thread([&] { distance_field(off, adj, N, coastline.items, stop.data(), seed + 3, hd[2]); });
-            th[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
-            distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]);
-            for (auto& t : th) t.join();
-        }
+        std::thread fill[5];
+        fill[0] = std::thread([&] { distance_field(off, adj, N, stressMountain, ocean.in.data(), seed + 1, hd[0]); });
+        fill[1] = std::thread([&] { distance_field(off, adj, N, ocean.items, coastline.in.data(), seed + 2, hd[1]); });
+        fill[2] = std::thread([&] { distance_field(off, adj, N, coastline.items, stop.data(), seed + 3, hd[2]); });
+        fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
+        fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
+        struct Joiner { std::thread* t; int n; ~Joiner() { for (int k = 0; k < n; k++) if (t[k].joinable()) t[k].join(); } } joinFills{fill, 5};
 
-        lap("5 distance fills (threads)");
         // 6. maxStress = p97 of the non-trivial stresses (:443-453)
         double maxStress = 0;
         {
@@ -287,7 +287,7 @@ struct Elevation {
         const double maxCD = std::max(8.0, jsr(8 * scaleFactor));
         std::vector<float> hBdry(N, (float)(maxCD + 1)), hCS(N, 0.f), hCSub(N, 0.f);
         std::vector<uint8_t> hConv(N, 0);
-        {
+        std::thread coastBfs([&] {
             std::vector<int> q;
             for (int r = 0; r < N; r++) {
                 const uint8_t rOc = isOcean[r];
@@ -308,7 +308,8 @@ struct Elevation {
                     else if (nd == (double)hBdry[nr] && hCS[r] > hCS[nr]) { hCS[nr] = hCS[r]; hCSub[nr] = hCSub[r]; hConv[nr] = hConv[r]; }
                 }
             }
-        }
+        });
+        Joiner joinCoast{&coastBfs, 1};
         // generic capped BFS: pass(r, nr) decides whether nr may be entered from r; payload copied from the discoverer
         auto capped = [&](std::vector<float>& d, std::vector<float>* payload, std::vector<int>& q, double cap, int mode) {
             for (size_t qi = 0; qi < q.size();) {
@@ -341,8 +342,10 @@ struct Elevation {
             { std::vector<int> q; for (int r = 0; r < N; r++) if (btype[r] == 1 && bothOcean[r] && (double)sub[r] < 0.45) { q.push_back(r); hArc[r] = 0; hArcS[r] = norm(r); } capped(hArc, &hArcS, q, maxArcDist, 3); }
             t1.join(); t2.join(); t3.join(); t4.join();
         }
+        coastBfs.join();
+        for (auto& t : fill) t.join();
 
-        lap("p97 + capped BFS (threads)");
+        lap("fills + p97 + capped BFS (threads)");
         // 8. hotspot domes (:1148-1262)
         std::vector<DomeDev> domes;
         build_domes(P, r_plate, seed, domes);

@@ -394,7 +394,9 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     const int N = a.g.N;
     const unsigned FULL = 0xffffffffu;
     if (tid == 0) { done = 0; reqSeq = 0; respSeq = 0; respCount = 0; }
-    for (int w = tid; w < 64; w += blockDim.x) sh[w].c = 0;                  // helpers may peek before the first push
+    // every shared slot starts as a (+inf, 0) sentinel and slots beyond the live heap are kept that way, so
+    // the sift-down needs no bounds checks while the heap occupies less than half of the shared array
+    for (int w = tid; w < a.cap + 2; w += blockDim.x) { sh[w].k = 0x7f800000u; sh[w].c = 0; }
     __syncthreads();
 
     if (warp == 1) {
@@ -499,7 +501,23 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
         // pop: MinHeap.pop (:27-46) — last → root, sift down along the min-child path (left child on ties)
         --n;
         const HeapEntry last = n < cap ? sh[n + 1] : H.ld(n);
-        if (n > 0) {
+        if (n < cap) { HeapEntry inf; inf.k = 0x7f800000u; inf.c = 0; sh[n + 1] = inf; }     // keep the sentinel invariant
+        if (n > 0 && 2 * n + 4 < cap) {
+            // common case: every child index is inside the shared array and reads as +inf beyond the heap
+            const float kl = __uint_as_float(last.k);
+            int i = 0;
+            for (;;) {
+                const int l = 2 * i + 1;
+                const uint4 v = *(const uint4*)(sh + l + 1);
+                const bool right = __uint_as_float(v.z) < __uint_as_float(v.x);      // left child wins ties
+                const uint32_t mk = right ? v.z : v.x;
+                if (!(__uint_as_float(mk) < kl)) break;
+                HeapEntry m; m.k = mk; m.c = (int)(right ? v.w : v.y);
+                sh[i + 1] = m;
+                i = l + (right ? 1 : 0);
+            }
+            sh[i + 1] = last;
+        } else if (n > 0) {
             const float kl = __uint_as_float(last.k);
             int i = 0;
             bool placed = false;
