@@ -46,7 +46,7 @@ struct Climate {
         if (passes <= 0) return;
         float* src = field; float* dst = m->tmp.ensure(N);
         for (int p = 0; p < passes; p++) {
-            ex().for_each(N, SmoothMaskedK{csr(), mask, src, dst, zeroOutside ? 1 : 0});
+            if (!m->sweep_tiled(1, src, dst, mask, nullptr, zeroOutside)) ex().for_each(N, SmoothMaskedK{csr(), mask, src, dst, zeroOutside ? 1 : 0});
             std::swap(src, dst);
         }
         if (src != field) dev_copy(field, src, sizeof(float) * (size_t)N, 2, ex().stream);
@@ -324,7 +324,10 @@ struct Climate {
             const float* warmth = cF("r_ocean_warmth_" + name);
             float* src = a0.ensure(N); float* dst = a1.ensure(N);
             x.for_each(N, CoastalSeedK{cU("r_isLand"), warmth, src});
-            for (int p = 0; p < passes; p++) { x.for_each(N, DiffuseWarmthK{g, pcont, src, dst}); std::swap(src, dst); }
+            for (int p = 0; p < passes; p++) {
+                if (!m->sweep_tiled(2, src, dst, nullptr, pcont, false)) x.for_each(N, DiffuseWarmthK{g, pcont, src, dst});
+                std::swap(src, dst);
+            }
             float* temp = F("r_temperature_" + name);
             x.for_each(N, TemperatureK{cF("r_lat"), cF("r_lon"), cU("r_isLand"), elev, cF("r_continentality"), pcont,
                                        cF(s == 0 ? "itczLatsSummer" : "itczLatsWinter"), warmth, cF("r_ocean_speed_" + name),
