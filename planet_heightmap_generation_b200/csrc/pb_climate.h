@@ -294,6 +294,36 @@ struct BfsLevelK {
         }
     }
 };
+#if PB_CUDA
+}  // namespace pb
+#include <cooperative_groups.h>
+namespace pb {
+// All levels of one BFS in a single cooperative launch: one grid-wide barrier per level instead of one kernel
+// launch per level (a BFS at 1M cells has 100–300 levels of a few thousand cells each — launch-latency bound).
+__global__ void __launch_bounds__(256) k_bfs_persistent(Csr g, const uint8_t* passable, int* dist, int* frontA, int* frontB, int* cnt) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    int* cur = frontA; int* nxt = frontB;
+    for (int level = 0;; level++) {
+        const int n = ld_volatile(cnt + level % 3);
+        if (n == 0) break;
+        if (gtid == 0) cnt[(level + 2) % 3] = 0;
+        const int d = level + 1;
+        int* slot = cnt + (level + 1) % 3;
+        for (int i = gtid; i < n; i += stride) {
+            const int r = __ldcg(cur + i);      // written by other SMs in the previous level: read through L2
+            for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) {
+                const int nb = g.adj[j];
+                if (passable[nb] && ld_volatile(dist + nb) == -1 && atomicCAS(dist + nb, -1, d) == -1) nxt[atomicAdd(slot, 1)] = nb;
+            }
+        }
+        grid.sync();
+        int* t = cur; cur = nxt; nxt = t;
+    }
+}
+#endif
+
 // seeds: land cells touching the main ocean component (wind.js:514-523)
 struct LandCoastSeedK {
     Csr g; const uint8_t* isLand; const uint8_t* isOcean; const int* parent; const unsigned long long* best; int* dist; uint8_t* flag;

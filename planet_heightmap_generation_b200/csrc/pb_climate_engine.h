@@ -18,6 +18,7 @@ struct Climate {
     std::map<std::string, size_t> count;     // elements of every published field
     std::map<std::string, int> kind;         // 0 f32, 1 i32, 2 u8
     bool haveWind = false, haveOcean = false, havePrecip = false, haveTemp = false;
+    int bfsGrid = -1;
 
     // scratch
     DevBuf<float> sElev, a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, upWt, dnWt;
@@ -58,6 +59,24 @@ struct Climate {
         cnt.ensure(160); frontA.ensure(N); frontB.ensure(N);
         dev_memset(cnt.p, 0, 4 * sizeof(int), x.stream);
         m->prims.compact_flagged(x, seedFlag, N, frontA.p, cnt.p + 0);
+#if PB_CUDA
+        if (bfsGrid < 0) {
+            int perSm = 0, dev = 0, coop = 0;
+            PB_CUDA_CHECK(cudaGetDevice(&dev));
+            PB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+            PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_persistent, 256, 0));
+            bfsGrid = coop ? x.sm_count * std::min(perSm, 4) : 0;
+        }
+        if (bfsGrid > 0) {
+            Csr g = csr();
+            int* fa = frontA.p; int* fb = frontB.p; int* c = cnt.p;
+            void* args[] = {&g, (void*)&passable, &dist, &fa, &fb, &c};
+            launch_stats().launches++;
+            ProfScope ps(x.prof, "pb::k_bfs_persistent", x.stream);
+            PB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_persistent, dim3(bfsGrid), dim3(256), args, 0, x.stream));
+            return;
+        }
+#endif
         int* cur = frontA.p; int* nxt = frontB.p;
         const int CHECK = 16;
         for (int level = 0;; level++) {
