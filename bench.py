@@ -302,8 +302,9 @@ def run_b200(args):
 
     wl = args.workload
     do_elev, do_post, do_clim = wl in ("full", "elevation"), wl in ("full", "post"), wl in ("full", "climate")
-    # replicas: every rank processes its own planet (same mesh, different plates / terrain seed)
-    inp = Inputs(args.cells, SEED + rank)
+    # replicas: every rank processes its own copy of the same seeded planet (identical work per GPU, so the
+    # N-GPU numbers are a clean weak-scaling series)
+    inp = Inputs(args.cells, SEED)
     mesh, xyz = inp.mesh, inp.xyz
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
     dm = DeviceMesh(mesh, xyz, device=local)
@@ -486,7 +487,7 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.cells, args.hiters, wl), "cells_per_gpu": N,
-                       "multi_gpu": "replicas (one planet per GPU, no data-path collective)" if world > 1 else "single",
+                       "multi_gpu": "replicas (one copy of the planet per GPU, no data-path collective)" if world > 1 else "single",
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
                        "flood": args.flood or "device",
@@ -503,6 +504,10 @@ def run_b200(args):
 
 
 def main():
+    # exactly one line on stdout: libraries (NCCL's version banner, …) that write to fd 1 are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
