@@ -65,7 +65,7 @@ struct Climate {
             PB_CUDA_CHECK(cudaGetDevice(&dev));
             PB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
             PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_persistent, 256, 0));
-            bfsGrid = coop ? x.sm_count * std::min(perSm, 4) : 0;
+            bfsGrid = (coop && perSm > 0) ? x.sm_count : 0;      // one CTA per SM: frontiers are small, the grid barrier is the cost
         }
         if (bfsGrid > 0) {
             Csr g = csr();

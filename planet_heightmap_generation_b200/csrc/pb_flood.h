@@ -586,6 +586,7 @@ struct CarveLiftArgs {
     const int* up; int levels; int N; const int* depth; double carveStrength;
 };
 #define PB_CARVE_THREADS 256
+#define PB_CARVE_PATH_CAP 2048
 
 __device__ __forceinline__ int lift_ancestor(const int* up, int N, int c, int j) {
     for (int k = 0; j; k++, j >>= 1) if (j & 1) c = __ldg(up + (size_t)k * N + c);
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(PB_CARVE_THREADS) k_carve_lift(CarveLiftArgs a
     __shared__ int sRedJ[PB_CARVE_THREADS / 32];
     __shared__ double sTerm[PB_CARVE_THREADS];
     __shared__ double sKernelSum;
+    __shared__ int sPath[PB_CARVE_PATH_CAP];      // ancestors of the current cell (the window pass reuses them)
     int q0 = segB;
     while (q0 < segE) {
         // find the next cell (ascending id) whose current deficit exceeds EPS
@@ -626,6 +628,7 @@ __global__ void __launch_bounds__(PB_CARVE_THREADS) k_carve_lift(CarveLiftArgs a
         double bh = -INFINITY; int bj = 0x7fffffff;
         for (int j = tid; j < len; j += PB_CARVE_THREADS) {
             const int c = lift_ancestor(a.up, a.N, r, j);
+            if (j < PB_CARVE_PATH_CAP) sPath[j] = c;
             const double h = (double)__ldcg(a.elev + c);
             if (h > bh) { bh = h; bj = j; }
         }
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(PB_CARVE_THREADS) k_carve_lift(CarveLiftArgs a
         const double kernelSum = sKernelSum;
         if (kernelSum > 0) {
             for (int k = startIdx + tid; k <= endIdx; k += PB_CARVE_THREADS) {
-                const int c = lift_ancestor(a.up, a.N, r, k);
+                const int c = k < PB_CARVE_PATH_CAP ? sPath[k] : lift_ancestor(a.up, a.N, r, k);
                 const double dist = k > peakIdx ? k - peakIdx : peakIdx - k;
                 const double weight = (1 - dist / (radius + 1)) / kernelSum;
                 float v = (float)((double)__ldcg(a.elev + c) - carveAmount * weight);

@@ -73,3 +73,37 @@ def test_pair_intensity_js_semantics(oracle):
         return 0.5 + (h % 10001) / 10000
     for a, b in [(3, 17), (19999, 12345), (0, 1), (18000, 18001), (7, 7), (123456, 654321)]:
         assert oracle.pair_intensity(a, b) == ref(a, b)
+
+
+@pytest.mark.parametrize("kind", ["all_land", "all_ocean", "zero_omega"])
+def test_assign_elevation_edge_cases(backend, oracle, kind):
+    """No oceanic plate at all (empty ocean seed set → infinite ocean distances), no continental plate, and plates
+    that do not move (no collisions → empty mountain set, hotspot chains skipped for driftLen < 1e-6)."""
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    mesh, xyz, r_plate, plates, seeds, r_super, sp = _inputs(oracle, 3000)
+    plates = {p: dict(v) for p, v in plates.items()}
+    for v in plates.values():
+        if kind == "all_land":
+            v["isOcean"] = False
+        elif kind == "all_ocean":
+            v["isOcean"] = True
+        else:
+            v["omega"] = 0.0
+    oe = oracle.Elevation(mesh, xyz)
+    oe.assign(r_plate, plates, seeds, 42, 0.4, 42, 5)
+    got = _call(DeviceMesh(mesh, xyz, lib=backend), xyz, r_plate, plates, seeds, 42, 0.4, 42, 5)
+    assert_bit_equal(got["r_elevation"], oe.get("r_elevation"), "r_elevation " + kind)
+    assert_bit_equal(got["r_stress"], oe.get("r_stress"), "r_stress " + kind)
+    for k in ("mountain_r", "coastline_r", "ocean_r"):
+        assert_bit_equal(got[k], oe.get(k, np.uint8), k)
+    if kind == "zero_omega":
+        assert got["mountain_r"].sum() == 0 and oe.get("domes").size == 0
+
+
+def test_assign_elevation_rejects_unknown_plate_id(backend, oracle):
+    from planet_heightmap_generation_b200._lib import PlanetB200Error
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    mesh, xyz, r_plate, plates, seeds, r_super, sp = _inputs(oracle, 3000)
+    bad = r_plate.copy(); bad[5] = 10 ** 6
+    with pytest.raises(PlanetB200Error):
+        _call(DeviceMesh(mesh, xyz, lib=backend), xyz, bad, plates, seeds, 42, 0.4, 42, 5)
