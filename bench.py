@@ -503,6 +503,76 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# sharded sweeps: the one data path that has a real exchange step (cell-range shards + one-cell halo per sweep)
+# ---------------------------------------------------------------------------------------------------
+def run_sharded_sweeps(args):
+    """`--workload sharded-sweeps`: smoothField (js/climate-util.js:5-25) over a mesh sharded by contiguous cell-id
+    ranges across the ranks, one halo exchange (torch.distributed p2p over NCCL) per sweep.  Strong scaling of one
+    planet: value = cells × sweeps per second."""
+    import torch
+    import torch.distributed as dist
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    from planet_heightmap_generation_b200.sharded import HaloExchanger, Shard, smoothFieldSharded
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    mesh, xyz = get_planet(args.cells)
+    N = mesh.numRegions
+    field0 = synthetic_elevation(xyz, SEED, 0.3)
+    sh = Shard(mesh, xyz, world, rank)
+    dm = DeviceMesh(sh.mesh, sh.r_xyz, device=local)
+    ex = HaloExchanger(sh, dev)
+    f0 = torch.from_numpy(sh.scatter(field0)).to(dev)
+    f = f0.clone()
+    sweeps = args.sweeps
+
+    def step():
+        f.copy_(f0)
+        smoothFieldSharded(dm, ex, f, sweeps) if world > 1 else __import__(
+            "planet_heightmap_generation_b200.climate_util", fromlist=["smoothField"]).smoothField(dm, f, sweeps)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        per_sweep_us = 1000 * ms / (args.steps * sweeps)
+        print(json.dumps({
+            "metric": "cell_sweeps_per_sec_sharded_smoothField", "value": N * sweeps * args.steps / (ms / 1000), "unit": "cell-sweeps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{N}-cell sphere, {sweeps} smoothField sweeps per step, cell-range shards, one-cell halo "
+                                   f"exchange per sweep over NCCL p2p", "us_per_sweep": per_sweep_us,
+                       "halo_cells_rank0": int(sh.halo.size), "halo_bytes_per_sweep_rank0": sh.halo_bytes_per_sweep,
+                       "peers_rank0": sorted(sh.recv)},
+            "algorithmic_GBps": 36.0 * N / (per_sweep_us * 1e-6) / 1e9}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     # exactly one line on stdout: libraries (NCCL's version banner, …) that write to fd 1 are sent to stderr
     real_stdout = os.dup(1)
@@ -513,7 +583,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "sharded-sweeps"])
+    ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],
                     help="engine option: where the serial heap pass of priorityFloodCarve runs (default device)")
     ap.add_argument("--cells", type=int, default=1_000_000)
@@ -524,7 +595,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: fewer than 3 warm-up steps requested")
-    if args.impl == "reference":
+    if args.workload == "sharded-sweeps":
+        run_sharded_sweeps(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
