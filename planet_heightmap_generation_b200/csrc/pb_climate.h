@@ -481,6 +481,16 @@ struct SmoothMaskedK {
     PB_DEV void operator()(int r) const {
         if (!mask[r]) { dst[r] = zeroOutside ? 0.0f : src[r]; return; }
         double sum = src[r]; int count = 1;
+        RowIds row;
+        if (row.load(g, r)) {
+            float v[PB_ROW_FAST]; uint8_t mk[PB_ROW_FAST];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) { v[k] = src[row.nb[k]]; mk[k] = mask[row.nb[k]]; }
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) if (k < row.deg && mk[k]) { sum += v[k]; count++; }
+            dst[r] = (float)(sum / count);
+            return;
+        }
         for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) {
             const int nb = g.adj[j];
             if (mask[nb]) { sum += src[nb]; count++; }
@@ -494,6 +504,16 @@ struct DiffuseWarmthK {
     PB_DEV void operator()(int r) const {
         if ((double)pcont[r] >= 0.95) { dst[r] = src[r]; return; }
         double sum = src[r]; int count = 1;
+        RowIds row;
+        if (row.load(g, r)) {
+            float v[PB_ROW_FAST];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) if (k < row.deg) sum += v[k];
+            dst[r] = (float)(sum / (row.deg + 1));
+            return;
+        }
         for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) { sum += src[g.adj[j]]; count++; }
         dst[r] = (float)(sum / count);
     }
@@ -930,6 +950,18 @@ struct ShadowSweepK {
         const float s = src[r];
         if (!isLand[r]) { dst[r] = s; return; }
         double val = 0, w = 0;
+        RowIds row;
+        if (row.load(g, r)) {
+            float wk[PB_ROW_FAST], v[PB_ROW_FAST];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) { wk[k] = k < row.deg ? wt[row.b + k] : 0.0f; v[k] = src[row.nb[k]]; }
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++)
+                if (wk[k] > 0) {
+                    const double vv = v[k];
+                    if (sign < 0 ? (vv < 0) : (vv > 0)) { val += vv * (double)wk[k]; w += (double)wk[k]; }
+                }
+        } else
         for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) {
             const float wj = wt[j];
             if (wj > 0) {

@@ -29,11 +29,39 @@ struct NeighborDistK {
     }
 };
 
+// Row gather with memory-level parallelism.  A sweep thread that walks its row as `sum += src[adj[i]]` serialises
+// two dependent load latencies per neighbour (≈ 12 per cell): at full occupancy that, not bandwidth, bounds the
+// sweep (profiles/r01_sweeps_ncu.md).  The helpers below issue all neighbour-id loads of a row at once and then all
+// value gathers at once (rows of up to PB_ROW_FAST neighbours — every row of a spherical Delaunay mesh in practice;
+// longer rows take the plain loop), so a cell costs two load latencies.  The additions still run in adjacency
+// order, which keeps the f64 sums bit-identical.
+#define PB_ROW_FAST 8
+struct RowIds {
+    int nb[PB_ROW_FAST]; int b, deg;
+    PB_DEV bool load(const Csr& g, int r) {       // returns false for rows longer than PB_ROW_FAST
+        b = g.off[r]; deg = g.off[r + 1] - b;
+        if (deg > PB_ROW_FAST) return false;
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) nb[k] = k < deg ? g.adj[b + k] : r;
+        return true;
+    }
+};
+
 // js/climate-util.js:5-25 — one Laplacian sweep  dst = (src[r] + Σ src[nb]) / (deg + 1)
 struct SmoothFieldK {
     Csr g; const float* src; float* dst;
     PB_DEV void operator()(int r) const {
+        RowIds row;
         double sum = src[r];
+        if (row.load(g, r)) {
+            float v[PB_ROW_FAST];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
+#pragma unroll
+            for (int k = 0; k < PB_ROW_FAST; k++) if (k < row.deg) sum += v[k];
+            dst[r] = (float)(sum / (row.deg + 1));
+            return;
+        }
         int count = 1;
         for (int i = g.off[r], e = g.off[r + 1]; i < e; i++) { sum += src[g.adj[i]]; count++; }
         dst[r] = (float)(sum / count);
