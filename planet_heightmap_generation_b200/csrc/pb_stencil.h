@@ -37,34 +37,30 @@ struct NeighborDistK {
 // order, which keeps the f64 sums bit-identical.
 #define PB_ROW_FAST 8
 struct RowIds {
-    int nb[PB_ROW_FAST]; int b, deg;
-    PB_DEV bool load(const Csr& g, int r) {       // returns false for rows longer than PB_ROW_FAST
-        b = g.off[r]; deg = g.off[r + 1] - b;
-        if (deg > PB_ROW_FAST) return false;
+    int nb[PB_ROW_FAST];
+    PB_DEV void load(int r, int deg, const int* ids) {       // deg <= PB_ROW_FAST
 #pragma unroll
-        for (int k = 0; k < PB_ROW_FAST; k++) nb[k] = k < deg ? g.adj[b + k] : r;
-        return true;
+        for (int k = 0; k < PB_ROW_FAST; k++) nb[k] = k < deg ? ids[k] : r;
     }
 };
 
 // js/climate-util.js:5-25 — one Laplacian sweep  dst = (src[r] + Σ src[nb]) / (deg + 1)
 struct SmoothFieldK {
     Csr g; const float* src; float* dst;
-    PB_DEV void operator()(int r) const {
-        RowIds row;
+    PB_DEV void operator()(int r) const { const int b = g.off[r]; row(r, b, g.off[r + 1] - b, g.adj + b); }
+    PB_DEV void row(int r, int b, int deg, const int* ids) const {
+        (void)b;
         double sum = src[r];
-        if (row.load(g, r)) {
+        if (deg <= PB_ROW_FAST) {
+            RowIds row; row.load(r, deg, ids);
             float v[PB_ROW_FAST];
 #pragma unroll
             for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
 #pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) if (k < row.deg) sum += v[k];
-            dst[r] = (float)(sum / (row.deg + 1));
-            return;
-        }
-        int count = 1;
-        for (int i = g.off[r], e = g.off[r + 1]; i < e; i++) { sum += src[g.adj[i]]; count++; }
-        dst[r] = (float)(sum / count);
+            for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg) sum += v[k];
+        } else
+            for (int i = 0; i < deg; i++) sum += src[ids[i]];
+        dst[r] = (float)(sum / (deg + 1));
     }
 };
 
