@@ -47,7 +47,7 @@ struct Climate {
         if (passes <= 0) return;
         float* src = field; float* dst = m->tmp.ensure(N);
         for (int p = 0; p < passes; p++) {
-            if (!m->sweep_tiled(1, src, dst, mask, nullptr, zeroOutside)) ex().for_each_row(N, m->off.p, m->adj.p, SmoothMaskedK{csr(), mask, src, dst, zeroOutside ? 1 : 0});
+            if (!m->sweep_tiled(1, src, dst, mask, nullptr, zeroOutside)) ex().for_each(N, SmoothMaskedK{csr(), mask, src, dst, zeroOutside ? 1 : 0});
             std::swap(src, dst);
         }
         if (src != field) dev_copy(field, src, sizeof(float) * (size_t)N, 2, ex().stream);
@@ -298,13 +298,13 @@ struct Climate {
             {
                 float* a = ping; float* b = pong;
                 dev_copy(a, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                for (int it = 0; it < shadowHops; it++) { x.for_each_row(N, m->off.p, m->adj.p, ShadowSweepK{g, isLand, upWt.p, a, b, 1 - shadowDecay, -1}); std::swap(a, b); }
+                for (int it = 0; it < shadowHops; it++) { x.for_each(N, ShadowSweepK{g, isLand, upWt.p, a, b, 1 - shadowDecay, -1}); std::swap(a, b); }
                 x.for_each(N, KeepExtremeK{a, shadowField, -1});
             }
             {
                 float* a = ping; float* b = pong;
                 dev_copy(a, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                for (int it = 0; it < windwardHops; it++) { x.for_each_row(N, m->off.p, m->adj.p, ShadowSweepK{g, isLand, dnWt.p, a, b, 1 - windwardDecay, +1}); std::swap(a, b); }
+                for (int it = 0; it < windwardHops; it++) { x.for_each(N, ShadowSweepK{g, isLand, dnWt.p, a, b, 1 - windwardDecay, +1}); std::swap(a, b); }
                 x.for_each(N, KeepExtremeK{a, windwardField, +1});
             }
             x.for_each(N, MergeShadowK{shadowField, windwardField, rainShadow});
@@ -344,7 +344,7 @@ struct Climate {
             float* src = a0.ensure(N); float* dst = a1.ensure(N);
             x.for_each(N, CoastalSeedK{cU("r_isLand"), warmth, src});
             for (int p = 0; p < passes; p++) {
-                if (!m->sweep_tiled(2, src, dst, nullptr, pcont, false)) x.for_each_row(N, m->off.p, m->adj.p, DiffuseWarmthK{g, pcont, src, dst});
+                if (!m->sweep_tiled(2, src, dst, nullptr, pcont, false)) x.for_each(N, DiffuseWarmthK{g, pcont, src, dst});
                 std::swap(src, dst);
             }
             float* temp = F("r_temperature_" + name);

@@ -222,7 +222,7 @@ struct Mesh {
         if (passes <= 0) return;
         float* src = field; float* dst = tmp.ensure(N);
         for (int p = 0; p < passes; p++) {
-            if (!sweep_tiled(0, src, dst, nullptr, nullptr, false)) ex().for_each_row(N, off.p, adj.p, SmoothFieldK{csr(), src, dst});
+            if (!sweep_tiled(0, src, dst, nullptr, nullptr, false)) ex().for_each(N, SmoothFieldK{csr(), src, dst});
             std::swap(src, dst);
         }
         if (src != field) dev_copy(field, src, sizeof(float) * (size_t)N, 2, ex().stream);

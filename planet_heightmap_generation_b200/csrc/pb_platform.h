@@ -289,30 +289,6 @@ PB_GLOBAL void k_single(F f) {
     f();
 }
 
-// Row executor for CSR sweeps: a CTA owns 256 consecutive cells, loads their slice of adjList into shared memory
-// with coalesced loads (one sector per ~8 edges instead of one sector per lane per neighbour slot) and hands each
-// thread its row as a shared-memory pointer.  F::row(r, b, deg, nb) — b = global edge index of the row start.
-#define PB_ROWS_THREADS 256
-#define PB_ROWS_CAP 2560
-template <class F>
-PB_GLOBAL void __launch_bounds__(PB_ROWS_THREADS) k_rows(F f, const int* off, const int* adj, int n) {
-    __shared__ int sAdj[PB_ROWS_CAP];
-    const int tid = threadIdx.x;
-    for (int c0 = blockIdx.x * PB_ROWS_THREADS; c0 < n; c0 += gridDim.x * PB_ROWS_THREADS) {
-        const int c1 = min(n, c0 + PB_ROWS_THREADS);
-        const int a0 = off[c0], cnt = off[c1] - a0;
-        const bool staged = cnt <= PB_ROWS_CAP;
-        if (staged) for (int i = tid; i < cnt; i += PB_ROWS_THREADS) sAdj[i] = adj[a0 + i];
-        __syncthreads();
-        const int r = c0 + tid;
-        if (r < c1) {
-            const int b = off[r], deg = off[r + 1] - b;
-            f.row(r, b, deg, staged ? sAdj + (b - a0) : adj + b);
-        }
-        __syncthreads();
-    }
-}
-
 // grid-stride loop whose bound lives in device memory (frontier sizes); global thread 0 first runs
 // the functor's block0() hook.
 template <class F>
@@ -361,22 +337,6 @@ struct Exec {
         for (int i = 0; i < n; i++) {
             if (!f.try_run(i)) throw Error("ordered dataflow: dependency of a later item (emulation)");
         }
-#endif
-    }
-
-    // f.row(r, b, deg, nb) for every cell r of the CSR graph (adjacency staged through shared memory on the GPU)
-    template <class F>
-    void for_each_row(int n, const int* off, const int* adj, const F& f) const {
-        if (n <= 0) return;
-        launch_stats().launches++;
-        ProfScope ps(prof, typeid(F).name(), stream);
-#if PB_CUDA
-        long long want = ((long long)n + PB_ROWS_THREADS - 1) / PB_ROWS_THREADS;
-        int grid = (int)std::min<long long>(want, (long long)sm_count * 8);
-        k_rows<F><<<grid, PB_ROWS_THREADS, 0, stream>>>(f, off, adj, n);
-        PB_CUDA_CHECK(cudaGetLastError());
-#else
-        for (int r = 0; r < n; r++) f.row(r, off[r], off[r + 1] - off[r], adj + off[r]);
 #endif
     }
 
