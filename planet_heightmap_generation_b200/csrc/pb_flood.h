@@ -386,62 +386,79 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HeapEntry* sh = (HeapEntry*)smem_raw;                                  // [cap + 2]
     __shared__ volatile int done;
-    // mailbox between the heap warp and the expansion warp
-    __shared__ volatile int reqSeq, reqCell, respSeq, respCount;
-    __shared__ volatile uint32_t respKey[32];
-    __shared__ volatile int respCell[32];
+    // mailboxes between the heap warp (warp 0) and the two expansion warps (warps 1 and 2; pop #t goes to warp 1 + t%2)
+    __shared__ volatile int reqSeq, reqCell;          // "pop #reqSeq is cell reqCell"
+    __shared__ volatile int candSeq, candCell;        // "pop #candSeq will probably be cell candCell" (root after the previous sift-down)
+    __shared__ volatile int respSeq[2], respCount[2];
+    __shared__ volatile uint32_t respKey[2][32];
+    __shared__ volatile int respCell[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = a.g.N;
     const unsigned FULL = 0xffffffffu;
-    if (tid == 0) { done = 0; reqSeq = 0; respSeq = 0; respCount = 0; }
+    if (tid == 0) { done = 0; reqSeq = 0; candSeq = 0; candCell = -1; respSeq[0] = respSeq[1] = 0; respCount[0] = respCount[1] = 0; }
     // every shared slot starts as a (+inf, 0) sentinel and slots beyond the live heap are kept that way, so
     // the sift-down needs no bounds checks while the heap occupies less than half of the shared array
     for (int w = tid; w < a.cap + 2; w += blockDim.x) { sh[w].k = 0x7f800000u; sh[w].c = 0; }
     __syncthreads();
 
-    if (warp == 1) {
-        // ---- expansion warp: lane j owns neighbour j of the cell the heap warp is popping.  It reads the
-        // CSR row, the visited flags, elevations and noise, decides fill / no fill, writes surface, drainTo
-        // and visited, and hands the new (key, cell) pairs back in adjacency order.  All of this overlaps
-        // the heap warp's sift-down.
-        for (int t = 1;; t++) {
-            while (reqSeq != t) { if (done) return; }
-            const int r = reqCell;
-            const int b = __ldg(a.g.off + r), e = __ldg(a.g.off + r + 1);
-            const double surfR = (double)__ldcg(a.surface + r);
-            uint32_t kbits = 0; int nb = -1; bool fresh = false;
-            if (b + lane < e) {
-                nb = __ldg(a.g.adj + b + lane);
-                const bool v = __ldcg(a.visited + nb) != 0;
-                const float el = __ldg(a.elev + nb);
-                const float k0 = __ldg(a.key0 + nb);
-                const double noise = __ldg(a.noise + nb);
-                if (!v) {
-                    fresh = true;
-                    float kf = k0;
-                    if ((double)el < surfR + PB_FLOOD_EPS) {
-                        const float s = (float)(surfR + PB_FLOOD_EPS);
-                        __stcg(a.surface + nb, s);
-                        kf = (float)((double)s + noise);
-                    }
-                    kbits = __float_as_uint(kf);
-                    __stcg(a.drainTo + nb, r);
-                    __stcg(a.visited + nb, (uint8_t)1);
+    if (warp == 1 || warp == 2) {
+        // ---- expansion warps: lane j owns neighbour j of the popped cell.  A warp reads the CSR row, elevations,
+        // initial keys and noise of the cell it EXPECTS to be popped next-but-one as soon as the heap warp has
+        // published that candidate (the root left by the previous sift-down), i.e. while the other expansion warp
+        // and the heap warp are still busy with the pop before.  When the real request arrives it only has to
+        // re-read the visited flags (the other warp may just have claimed a shared neighbour), decide fill / no
+        // fill, write surface / drainTo / visited and hand the new (key, cell) pairs back in adjacency order.
+        const int me = warp - 1;
+        for (int t = 1 + me;; t += 2) {
+            // phase A: static data of the candidate (or of the real cell if the request is already there)
+            int c = -1;
+            for (;;) {
+                if (reqSeq >= t) { c = reqCell; break; }
+                if (candSeq >= t) { c = candCell; break; }
+                if (done) return;
+            }
+            int b = 0, e = 0, nb = -1; float surfRf = 0.f, el = 0.f, k0 = 0.f; double noise = 0;
+            auto load_static = [&](int cell) {
+                b = __ldg(a.g.off + cell); e = __ldg(a.g.off + cell + 1);
+                surfRf = __ldcg(a.surface + cell);
+                nb = -1;
+                if (b + lane < e) {
+                    nb = __ldg(a.g.adj + b + lane);
+                    el = __ldg(a.elev + nb); k0 = __ldg(a.key0 + nb); noise = __ldg(a.noise + nb);
                 }
+            };
+            if (c >= 0) load_static(c);
+            // phase B: the real request
+            while (reqSeq < t) { if (done) return; }
+            __threadfence_block();
+            const int r = reqCell;
+            if (r != c) load_static(r);
+            const double surfR = (double)surfRf;
+            uint32_t kbits = 0; bool fresh = false;
+            if (nb >= 0 && __ldcg(a.visited + nb) == 0) {
+                fresh = true;
+                float kf = k0;
+                if ((double)el < surfR + PB_FLOOD_EPS) {
+                    const float s = (float)(surfR + PB_FLOOD_EPS);
+                    __stcg(a.surface + nb, s);
+                    kf = (float)((double)s + noise);
+                }
+                kbits = __float_as_uint(kf);
+                __stcg(a.drainTo + nb, r);
+                __stcg(a.visited + nb, (uint8_t)1);
             }
             const unsigned m = __ballot_sync(FULL, fresh);
-            if (fresh) { const int slot = __popc(m & ((1u << lane) - 1)); respKey[slot] = kbits; respCell[slot] = nb; }
-            if (lane == 0) respCount = __popc(m);
+            if (fresh) { const int slot = __popc(m & ((1u << lane) - 1)); respKey[me][slot] = kbits; respCell[me][slot] = nb; }
+            if (lane == 0) respCount[me] = __popc(m);
             __syncwarp();
             __threadfence_block();
-            if (lane == 0) respSeq = t;
+            if (lane == 0) respSeq[me] = t;
         }
     }
-    if (warp > 1) {
-        // ---- prefetch helpers: keep the rows of the heap's top entries hot in L1 -------------------
-        const int nHelpers = (blockDim.x >> 5) - 2;
+    if (warp > 2) {
+        // ---- prefetch helper: keep the rows of the heap's top entries hot in L1 -------------------
         while (!done) {
-            for (int idx = warp - 2; idx < 15; idx += nHelpers) {
+            for (int idx = 0; idx < 15; idx++) {
                 int c = ((volatile HeapEntry*)sh)[idx + 1].c;
                 if (c < 0 || c >= N) continue;
                 const int b = __ldg(a.g.off + c), e = __ldg(a.g.off + c + 1);
@@ -497,36 +514,44 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     for (int t = 1; n > 0; t++) {
         if (n > maxN) maxN = n;
         // hand the popped cell to the expansion warp, then restore the heap while it works
-        if (lane == 0) { reqCell = sh[1].c; __threadfence_block(); reqSeq = t; }
+        if (lane == 0) { reqCell = sh[1].c; reqSeq = t; }      // volatile shared stores stay in program order
         // pop: MinHeap.pop (:27-46) — last → root, sift down along the min-child path (left child on ties)
         --n;
         const HeapEntry last = n < cap ? sh[n + 1] : H.ld(n);
         if (n < cap) { HeapEntry inf; inf.k = 0x7f800000u; inf.c = 0; sh[n + 1] = inf; }     // keep the sentinel invariant
-        if (n > 0 && 2 * n + 4 < cap) {
-            // common case: every child index is inside the shared array and reads as +inf beyond the heap
+        if (n > 0 && 4 * n + 12 < cap) {
+            // small heap: every grandchild index is inside the (sentinel-padded) shared array, so the pairs below BOTH
+            // children are loaded one level ahead — the dependent chain per level is compare → select → compare
+            // instead of compare → address → shared-memory load (≈ 30 instead of ≈ 100 cycles per level).
             const float kl = __uint_as_float(last.k);
-            int i = 0;
+            int i = 0, l = 1;
+            uint4 P = *(const uint4*)(sh + l + 1);
+            uint4 QL = *(const uint4*)(sh + (2 * l + 1) + 1);
+            uint4 QR = *(const uint4*)(sh + (2 * l + 3) + 1);
             for (;;) {
-                const int l = 2 * i + 1;
-                const uint4 v = *(const uint4*)(sh + l + 1);
-                const bool right = __uint_as_float(v.z) < __uint_as_float(v.x);      // left child wins ties
-                const uint32_t mk = right ? v.z : v.x;
+                const bool right = __uint_as_float(P.z) < __uint_as_float(P.x);      // left child wins ties
+                const uint32_t mk = right ? P.z : P.x;
                 if (!(__uint_as_float(mk) < kl)) break;
-                HeapEntry m; m.k = mk; m.c = (int)(right ? v.w : v.y);
+                HeapEntry m; m.k = mk; m.c = (int)(right ? P.w : P.y);
                 sh[i + 1] = m;
                 i = l + (right ? 1 : 0);
+                P = right ? QR : QL;
+                l = 2 * i + 1;
+                QL = *(const uint4*)(sh + (2 * l + 1) + 1);
+                QR = *(const uint4*)(sh + (2 * l + 3) + 1);
             }
             sh[i + 1] = last;
         } else if (n > 0) {
+            // any heap size: children inside the shared array need no bounds check (slots beyond the heap hold +inf,
+            // and when the heap spills every shared slot is live); only the global tail takes the general loop
             const float kl = __uint_as_float(last.k);
             int i = 0;
             bool placed = false;
-            for (;;) {                                           // fast: both children in shared memory
+            for (;;) {
                 const int l = 2 * i + 1;
-                if (l >= n) { placed = true; break; }
                 if (l + 1 >= cap) break;
                 const uint4 v = *(const uint4*)(sh + l + 1);
-                const bool right = (l + 1 < n) && (__uint_as_float(v.z) < __uint_as_float(v.x));
+                const bool right = __uint_as_float(v.z) < __uint_as_float(v.x);      // left child wins ties
                 const uint32_t mk = right ? v.z : v.x;
                 if (!(__uint_as_float(mk) < kl)) { placed = true; break; }
                 HeapEntry m; m.k = mk; m.c = (int)(right ? v.w : v.y);
@@ -534,7 +559,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
                 i = l + (right ? 1 : 0);
             }
             if (!placed)
-                for (;;) {                                       // slow: children in the global tail
+                for (;;) {                                       // children in the global tail
                     const int l = 2 * i + 1;
                     if (l >= n) break;
                     const HeapEntry le = H.ld(l);
@@ -549,11 +574,13 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
             if (i < cap) sh[i + 1] = last; else H.st(i, last);
         }
         __syncwarp();
+        // the root now is the likely next pop: let the idle expansion warp start on its static data
+        if (lane == 0) { candCell = n > 0 ? sh[1].c : -1; candSeq = t + 1; }
         // push the cells the expansion warp discovered, in adjacency order
-        while (respSeq != t) {}
-        __threadfence_block();
-        const int cnt = respCount;
-        for (int k = 0; k < cnt; k++) push(respKey[k], respCell[k]);
+        const int w = (t + 1) & 1;              // pop #t was handled by expansion warp (t-1)%2 ... see `me` above
+        while (respSeq[w] != t) {}
+        const int cnt = respCount[w];
+        for (int k = 0; k < cnt; k++) push(respKey[w][k], respCell[w][k]);
         __syncwarp();
     }
     if (lane == 0) { done = 1; a.status[0] = maxN; }
