@@ -177,6 +177,20 @@ struct Elevation {
         stream_sync(x.stream);
         lap("collisions (device) + d2h");
 
+        // stress propagation (:329-362) only needs the raw collision outputs, so it starts now on its own threads and
+        // overlaps the set unions / blends / seed lists below
+        const double scaleFactor = sqrt(N / 10000.0);
+        const double baseDecay = 0.5 + spread * 0.04;
+        const double decayFactor = pb_pow(baseDecay, 1 / scaleFactor);
+        const double subductDecayFactor = pb_pow(baseDecay * 0.45, 1 / scaleFactor);
+        const int numPasses = (int)std::max(1.0, jsr(spread * 3 * scaleFactor));
+        std::vector<float> sSt(small.stress), sSu(small.subduct), pSt, pSu;
+        if (dual) { pSt = super.stress; pSu = super.subduct; }
+        std::thread prop[2];
+        prop[0] = std::thread([&] { propagate_stress(off, adj, N, sSt, sSu, r_plate, P, decayFactor, subductDecayFactor, numPasses); });
+        if (dual) prop[1] = std::thread([&] { propagate_stress(off, adj, N, pSt, pSu, r_super, *SP, decayFactor, subductDecayFactor, numPasses); });
+        struct Joiner { std::thread* t; int n; ~Joiner() { for (int k = 0; k < n; k++) if (t[k].joinable()) t[k].join(); } } joinProp{prop, 2};
+
         // 2. blend (:250-327)
         OrderedCells mountain, coastline, ocean;
         mountain.reset(N); coastline.reset(N); ocean.reset(N);
@@ -213,27 +227,7 @@ struct Elevation {
         }
 
         lap("sets + blend");
-        // 3. stress propagation (:329-362)
-        const double scaleFactor = sqrt(N / 10000.0);
-        const double baseDecay = 0.5 + spread * 0.04;
-        const double decayFactor = pb_pow(baseDecay, 1 / scaleFactor);
-        const double subductDecayFactor = pb_pow(baseDecay * 0.45, 1 / scaleFactor);
-        const int numPasses = (int)std::max(1.0, jsr(spread * 3 * scaleFactor));
-        if (!dual) propagate_stress(off, adj, N, stress, sub, r_plate, P, decayFactor, subductDecayFactor, numPasses);
-        else {
-            std::vector<float> sSt(small.stress), sSu(small.subduct), pSt(super.stress), pSu(super.subduct);
-            std::thread t1([&] { propagate_stress(off, adj, N, sSt, sSu, r_plate, P, decayFactor, subductDecayFactor, numPasses); });
-            propagate_stress(off, adj, N, pSt, pSu, r_super, *SP, decayFactor, subductDecayFactor, numPasses);
-            t1.join();
-            for (int r = 0; r < N; r++) {
-                stress[r] = (float)(SMALL_W * (double)sSt[r] + SUPER_W * (double)pSt[r]);
-                const double wS = SMALL_W * (double)sSt[r], wP = SUPER_W * (double)pSt[r], total = wS + wP;
-                if (total > 1e-6) sub[r] = (float)((wS * (double)sSu[r] + wP * (double)pSu[r]) / total);
-            }
-        }
-
-        lap("propagateStress");
-        // 4. plate representatives, seed sets (:368-388)
+        // 4a. plate representatives (need only the sets), ocean mask, coast seed lists — still overlapping the propagation
         {
             std::unordered_map<int, int> plateRep;
             for (int r = 0; r < N; r++) {
@@ -245,11 +239,6 @@ struct Elevation {
                 if (it != plateRep.end()) (P.ocean(pid) ? ocean : coastline).add(it->second);
             }
         }
-        std::vector<int> stressMountain;
-        std::vector<uint8_t> stop(N, 0);
-        for (int r : mountain.items) if ((double)sub[r] < 0.55) { stressMountain.push_back(r); stop[r] = 1; }
-        for (int r : coastline.items) stop[r] = 1;
-        for (int r : ocean.items) stop[r] = 1;
         std::vector<uint8_t> isOcean(N);
         for (int r = 0; r < N; r++) isOcean[r] = P.ocean(r_plate[r]) ? 1 : 0;
         OrderedCells coastSeeds; coastSeeds.reset(N);
@@ -258,8 +247,25 @@ struct Elevation {
             if (isOcean[r]) continue;
             for (int j = off[r], e = off[r + 1]; j < e; j++) if (isOcean[adj[j]]) { coastSeeds.add(adj[j]); landCoastSeeds.push_back(r); break; }
         }
-
         lap("representatives + seeds");
+        // 3. join the propagation, blend its results (:343-361)
+        prop[0].join();
+        if (dual) prop[1].join();
+        if (!dual) { stress = sSt; sub = sSu; }
+        else {
+            for (int r = 0; r < N; r++) {
+                stress[r] = (float)(SMALL_W * (double)sSt[r] + SUPER_W * (double)pSt[r]);
+                const double wS = SMALL_W * (double)sSt[r], wP = SUPER_W * (double)pSt[r], total = wS + wP;
+                if (total > 1e-6) sub[r] = (float)((wS * (double)sSu[r] + wP * (double)pSu[r]) / total);
+            }
+        }
+
+        lap("propagateStress");
+        std::vector<int> stressMountain;
+        std::vector<uint8_t> stop(N, 0);
+        for (int r : mountain.items) if ((double)sub[r] < 0.55) { stressMountain.push_back(r); stop[r] = 1; }
+        for (int r : coastline.items) stop[r] = 1;
+        for (int r : ocean.items) stop[r] = 1;
         // 5. five randomized fills (:392-426), each on its own thread; they run concurrently with the capped BFS below
         std::vector<float> hd[5];
         std::thread fill[5];
@@ -268,7 +274,7 @@ struct Elevation {
         fill[2] = std::thread([&] { distance_field(off, adj, N, coastline.items, stop.data(), seed + 3, hd[2]); });
         fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
         fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
-        struct Joiner { std::thread* t; int n; ~Joiner() { for (int k = 0; k < n; k++) if (t[k].joinable()) t[k].join(); } } joinFills{fill, 5};
+        Joiner joinFills{fill, 5};
 
         // 6. maxStress = p97 of the non-trivial stresses (:443-453)
         double maxStress = 0;
