@@ -229,14 +229,16 @@ struct Elevation {
         lap("sets + blend");
         // 4a. plate representatives (need only the sets), ocean mask, coast seed lists — still overlapping the propagation
         {
-            std::unordered_map<int, int> plateRep;
-            for (int r = 0; r < N; r++) {
+            std::vector<int> plateRep(P.n, -1);          // first unclaimed cell of every plate, by table row
+            int missing = P.n;
+            for (int r = 0; r < N && missing > 0; r++) {
                 if (mountain.in[r] || coastline.in[r] || ocean.in[r]) continue;
-                plateRep.emplace(r_plate[r], r);       // keeps the first
+                const int k = P.find(r_plate[r]);
+                if (k >= 0 && plateRep[k] < 0) { plateRep[k] = r; missing--; }
             }
             for (int pid : plateSeeds) {
-                auto it = plateRep.find(pid);
-                if (it != plateRep.end()) (P.ocean(pid) ? ocean : coastline).add(it->second);
+                const int k = P.find(pid);
+                if (k >= 0 && plateRep[k] >= 0) (P.ocean(pid) ? ocean : coastline).add(plateRep[k]);
             }
         }
         std::vector<uint8_t> isOcean(N);
