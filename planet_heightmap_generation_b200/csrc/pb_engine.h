@@ -289,7 +289,7 @@ struct Mesh {
         }
         const int cap = ((int)(floodSmemMax / sizeof(HeapEntry)) - 4) & ~1;
         FloodHeapArgs a{csr(), elev, surface.p, drainTo.p, visited.p, key.p, cellNoiseBuf.p, seeds.p, counters.p + 0,
-                        heapSpill.ensure(N), cap, counters.p + 12};
+                        heapSpill.ensure(N), cap, counters.p + 12, getenv("PB_FLOOD_NO_PREFETCH") ? 0 : 1};
         launch_stats().launches++;
         ProfScope ps(x.prof, "pb::k_flood_heap", x.stream);
         k_flood_heap<<<1, PB_FLOOD_THREADS, floodSmemMax, x.stream>>>(a);

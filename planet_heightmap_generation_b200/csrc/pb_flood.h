@@ -362,6 +362,7 @@ struct FloodHeapArgs {
     const float* key0; const double* noise;   // initial keys f32(elev + cellNoise) and cellNoise per cell (FloodInitK)
     const int* seeds; const int* nSeeds; HeapEntry* spill; int cap;
     int* status;   // [0] max heap size reached
+    int prefetchWarp;   // 1: warp 3 keeps the rows of the heap top hot in L1
 };
 
 #define PB_FLOOD_THREADS 128
@@ -457,6 +458,7 @@ __global__ void __launch_bounds__(PB_FLOOD_THREADS, 1) k_flood_heap(FloodHeapArg
     }
     if (warp > 2) {
         // ---- prefetch helper: keep the rows of the heap's top entries hot in L1 -------------------
+        if (!a.prefetchWarp) return;
         while (!done) {
             for (int idx = 0; idx < 15; idx++) {
                 int c = ((volatile HeapEntry*)sh)[idx + 1].c;
