@@ -513,7 +513,7 @@ def run_sharded_sweeps(args):
     import torch
     import torch.distributed as dist
     from planet_heightmap_generation_b200.engine import DeviceMesh
-    from planet_heightmap_generation_b200.sharded import HaloExchanger, Shard, smoothFieldSharded
+    from planet_heightmap_generation_b200.sharded import HaloExchanger, PeerHaloSmoother, Shard, smoothFieldSharded
     from planet_heightmap_generation_b200.sphere import synthetic_elevation
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -528,15 +528,21 @@ def run_sharded_sweeps(args):
     field0 = synthetic_elevation(xyz, SEED, 0.3)
     sh = Shard(mesh, xyz, world, rank)
     dm = DeviceMesh(sh.mesh, sh.r_xyz, device=local)
-    ex = HaloExchanger(sh, dev)
+    ex = HaloExchanger(sh, dev) if (world > 1 and args.halo == "nccl") else None
+    peer = PeerHaloSmoother(dm, sh) if (world > 1 and args.halo == "peer") else None
     f0 = torch.from_numpy(sh.scatter(field0)).to(dev)
     f = f0.clone()
     sweeps = args.sweeps
+    from planet_heightmap_generation_b200.climate_util import smoothField
 
     def step():
         f.copy_(f0)
-        smoothFieldSharded(dm, ex, f, sweeps) if world > 1 else __import__(
-            "planet_heightmap_generation_b200.climate_util", fromlist=["smoothField"]).smoothField(dm, f, sweeps)
+        if peer is not None:
+            peer.smooth(f, sweeps)            # halo values stored into peer memory by the kernels, flags over NVLink
+        elif ex is not None:
+            smoothFieldSharded(dm, ex, f, sweeps)   # one torch.distributed p2p exchange per sweep
+        else:
+            smoothField(dm, f, sweeps)
 
     def barrier():
         torch.cuda.synchronize()
@@ -565,10 +571,16 @@ def run_sharded_sweeps(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{N}-cell sphere, {sweeps} smoothField sweeps per step, cell-range shards, one-cell halo "
-                                   f"exchange per sweep over NCCL p2p", "us_per_sweep": per_sweep_us,
+                                   f"exchange per sweep" + ("" if world == 1 else
+                                   " by peer-memory stores + flags (CUDA IPC over NVLink)" if peer is not None else " over NCCL p2p"),
+                       "halo": "none" if world == 1 else args.halo, "us_per_sweep": per_sweep_us,
                        "halo_cells_rank0": int(sh.halo.size), "halo_bytes_per_sweep_rank0": sh.halo_bytes_per_sweep,
                        "peers_rank0": sorted(sh.recv)},
             "algorithmic_GBps": 36.0 * N / (per_sweep_us * 1e-6) / 1e9}), flush=True)
+    if peer is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -585,6 +597,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "sharded-sweeps"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],
                     help="engine option: where the serial heap pass of priorityFloodCarve runs (default device)")
     ap.add_argument("--cells", type=int, default=1_000_000)

@@ -209,6 +209,24 @@ pb_status pb_compute_climate(pb_climate* climate, const float* r_elevation, cons
 pb_status pb_climate_field_info(pb_climate* climate, const char* name, int32_t* kind_out, int64_t* count_out);
 pb_status pb_climate_get(pb_climate* climate, const char* name, void* out);
 
+/* ---- cell-range shards with device-side halo exchange (no reference counterpart: the reference is one thread) ----
+ * One process per GPU.  `mesh` is the rank's LOCAL mesh: owned cells [0, nOwn) followed by the halo cells its rows
+ * read (halo rows empty), see planet_heightmap_generation_b200/sharded.py.  For every peer the caller gives the
+ * owned cells that peer reads (send list, local ids) and the offset at which this rank's block starts inside the
+ * peer's local field.  The shard's buffers are exported as CUDA IPC handles (4 x 64 bytes) and the peers' handles
+ * are connected once; afterwards pb_smooth_field_sharded runs `passes` smoothField sweeps (js/climate-util.js:5-25)
+ * in which every rank's kernels store their boundary values straight into the peers' halo slots over NVLink and
+ * synchronise through flags in peer memory — no NCCL call and no host round trip per sweep.  Results are
+ * bit-identical to pb_smooth_field on the unsharded mesh.  Device pointers only (PB_POINTER_DEVICE). */
+typedef struct pb_shard pb_shard;
+pb_status pb_shard_create(pb_mesh* mesh, int32_t nOwn, int32_t myRank, int32_t worldSize, int32_t nPeers,
+                          const int32_t* peerRanks, const int32_t* sendCounts, const int32_t* sendIdx,
+                          const int32_t* peerRecvOffset, pb_shard** out);
+void pb_shard_destroy(pb_shard* shard);
+pb_status pb_shard_export(pb_shard* shard, unsigned char* handles256);
+pb_status pb_shard_connect(pb_shard* shard, int32_t peerIndex, const unsigned char* handles256);
+pb_status pb_smooth_field_sharded(pb_shard* shard, float* field, int32_t passes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 #include "pb_engine.h"
 #include "pb_climate_engine.h"
 #include "pb_elevation_engine.h"
+#include "pb_shard.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -39,6 +40,11 @@ struct pb_mesh {
 };
 
 struct pb_climate { pb::Climate c; explicit pb_climate(pb::Mesh* m) : c(m) {} };
+#if PB_CUDA
+struct pb_shard { pb::Shard s; template <class... A> explicit pb_shard(A... a) : s(a...) {} };
+#else
+struct pb_shard { int unused; };
+#endif
 
 extern "C" {
 
@@ -389,6 +395,51 @@ pb_status pb_climate_get(pb_climate* climate, const char* name, void* out) {
         const void* src = k == 0 ? (const void*)c.cF(name) : k == 1 ? (const void*)c.cI(name) : (const void*)c.cU(name);
         pb::dev_copy(out, src, it->second * (k == 2 ? 1 : 4), m.hostMode() ? 1 : 2, m.ex().stream);
         m.finish();
+    });
+}
+
+// ---- shards ---------------------------------------------------------------------------------------------------
+pb_status pb_shard_create(pb_mesh* mesh, int32_t nOwn, int32_t myRank, int32_t world, int32_t nPeers, const int32_t* peerRanks,
+                          const int32_t* sendCounts, const int32_t* sendIdx, const int32_t* peerRecvOffset, pb_shard** out) {
+    return guard([&] {
+        need(mesh && out && nPeers >= 0 && (nPeers == 0 || (peerRanks && sendCounts && sendIdx && peerRecvOffset)), "bad argument");
+#if PB_CUDA
+        mesh->m.ctx->bind();
+        *out = new pb_shard(&mesh->m, nOwn, myRank, world, nPeers, peerRanks, sendCounts, sendIdx, peerRecvOffset);
+#else
+        (void)nOwn; (void)myRank; (void)world;
+        throw std::invalid_argument("device-side halo exchange needs the CUDA build");
+#endif
+    });
+}
+void pb_shard_destroy(pb_shard* shard) { delete shard; }
+pb_status pb_shard_export(pb_shard* shard, unsigned char* handles) {
+    return guard([&] {
+        need(shard && handles, "NULL argument");
+#if PB_CUDA
+        shard->s.m->ctx->bind(); shard->s.export_handles(handles);
+#endif
+    });
+}
+pb_status pb_shard_connect(pb_shard* shard, int32_t peerIndex, const unsigned char* handles) {
+    return guard([&] {
+        need(shard && handles, "NULL argument");
+#if PB_CUDA
+        shard->s.m->ctx->bind(); shard->s.connect(peerIndex, handles);
+#else
+        (void)peerIndex;
+#endif
+    });
+}
+pb_status pb_smooth_field_sharded(pb_shard* shard, float* field, int32_t passes) {
+    return guard([&] {
+        need(shard && field, "NULL argument");
+#if PB_CUDA
+        need(!shard->s.m->hostMode(), "pb_smooth_field_sharded takes device pointers (PB_POINTER_DEVICE)");
+        shard->s.m->ctx->bind(); shard->s.smooth_field(field, passes);
+#else
+        (void)passes;
+#endif
     });
 }
 

@@ -106,3 +106,49 @@ def smoothFieldSharded(dm_local, exchanger: HaloExchanger, field, passes: int):
         smoothField(dm_local, arg, 1)
         exchanger.exchange(field)
     return field
+
+
+class PeerHaloSmoother:
+    """smoothField over the sharded mesh with the halo exchange done by the kernels themselves: every rank's buffers
+    are exported through CUDA IPC and peers store their boundary values into them over NVLink (csrc/pb_shard.h).
+    Setup exchanges the recv offsets and IPC handles once over torch.distributed; the sweeps never touch the host."""
+
+    def __init__(self, dm_local, shard: Shard):
+        import ctypes as C
+
+        import torch.distributed as dist
+        self.dm, self.shard = dm_local, shard
+        lib = dm_local.lib
+        world, rank = shard.world, shard.rank
+        peers = sorted(set(shard.send) | set(shard.recv))
+        assert set(shard.send) == set(shard.recv), "the mesh graph is undirected: send and recv peers coincide"
+        # where does my block start inside each peer's local field?  (the peer's recv slice for me)
+        mine = {p: shard.recv[p][0] for p in peers}            # my recv-slice start for blocks coming from p
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        recv_offset = np.ascontiguousarray([everyone[p][rank] for p in peers], np.int32)
+        send_counts = np.ascontiguousarray([shard.send[p].size for p in peers], np.int32)
+        send_idx = np.ascontiguousarray(np.concatenate([shard.send[p] for p in peers]) if peers else np.zeros(0), np.int32)
+        peer_ranks = np.ascontiguousarray(peers, np.int32)
+        self._h = C.c_void_p()
+        lib.check(lib.dll.pb_shard_create(dm_local._mesh, shard.nOwn, rank, world, len(peers), peer_ranks.ctypes.data,
+                                          send_counts.ctypes.data, send_idx.ctypes.data, recv_offset.ctypes.data, C.byref(self._h)))
+        buf = (C.c_ubyte * 256)()
+        lib.check(lib.dll.pb_shard_export(self._h, buf))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf))
+        for i, p in enumerate(peers):
+            hb = (C.c_ubyte * 256).from_buffer_copy(handles[p])
+            lib.check(lib.dll.pb_shard_connect(self._h, i, hb))
+        dist.barrier()
+
+    def smooth(self, field, passes: int):
+        """field: torch CUDA float32 tensor with nLocal elements (owned + halo, halo current); updated in place."""
+        self.dm._begin(field)
+        self.dm.lib.check(self.dm.lib.dll.pb_smooth_field_sharded(self._h, field.data_ptr(), int(passes)))
+        return field
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.dm.lib.dll.pb_shard_destroy(self._h)
+            self._h = None
