@@ -53,9 +53,21 @@ def log(*a):
 # ---------------------------------------------------------------------------------------------------
 # synthetic planet (cached on local disk: both arms and every rank use the same mesh)
 # ---------------------------------------------------------------------------------------------------
-def get_planet(cells: int, seed: int = SEED):
-    from planet_heightmap_generation_b200.mesh import SphereMesh, build_sphere_from_points
-    from planet_heightmap_generation_b200.sphere import fibonacci_sphere
+def get_planet(cells: int, seed: int = SEED, on_device: int | None = None):
+    """Mesh + r_xyz of the seeded planet.  Own arm (`on_device` = GPU index): triangulated on that GPU by the
+    product path (DeviceMesh.from_points).  Reference arm: the CPU checker oracle/mesh_hull.py, cached on disk."""
+    from planet_heightmap_generation_b200.mesh import SphereMesh
+    from planet_heightmap_generation_b200.sphere import fibonacci_sphere, sphere_points
+    if on_device is not None:
+        from planet_heightmap_generation_b200.engine import DeviceMesh
+        xyz = sphere_points(cells, 0.75, seed)
+        t = time.time()
+        dm = DeviceMesh.from_points(xyz, device=on_device)
+        mesh = SphereMesh.from_csr(dm.adjOffset, dm.adjList)
+        dm.close()
+        log(f"[bench] {cells}-cell mesh triangulated on the GPU in {time.time() - t:.2f}s (first call, includes context creation)")
+        return mesh, xyz
+    from oracle.mesh_hull import build_sphere_from_points
     cache_dir = os.path.join(tempfile.gettempdir(), "planet_b200_cache")
     path = os.path.join(cache_dir, f"mesh_{cells}_{seed}.npz")
     if os.path.exists(path):
@@ -88,9 +100,9 @@ class Inputs:
     """What the hot path receives from the upstream stages (mesh construction, plate pipeline): mesh, r_xyz and
     the plate tables — here seeded synthetic stand-ins (sphere.synthetic_plate_tables)."""
 
-    def __init__(self, cells: int, seed: int = SEED):
+    def __init__(self, cells: int, seed: int = SEED, on_device: int | None = None):
         from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plate_tables
-        self.mesh, self.xyz = get_planet(cells, SEED)
+        self.mesh, self.xyz = get_planet(cells, SEED, on_device)
         hint = synthetic_elevation(self.xyz, seed, 0.3)       # only decides which plates are oceanic
         self.r_plate, self.plates, self.seeds, self.r_super, self.super_plates = synthetic_plate_tables(self.xyz, hint, seed)
         self.pio = {p for p, v in self.plates.items() if v["isOcean"]}
@@ -108,7 +120,9 @@ def workload_name(cells, hiters, workload):
     post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
             f"ridge 3, creep 3")
     clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
-    what = {"post": post, "climate": clim, "elevation": elev, "full": elev + " then " + post + " then " + clim}[workload]
+    tri = "spherical Delaunay adjacency of the points (buildSphere's triangulation + SphereMesh constructor)"
+    what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri,
+            "full": tri + " then " + elev + " then " + post + " then " + clim}[workload]
     return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
 
 
@@ -189,6 +203,15 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
         oe.assign(inp.r_plate, inp.plates, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.r_super, inp.super_plates)
         return oe.get("r_elevation"), oe.get("hotspot")
 
+    if workload == "mesh":
+        from oracle.mesh_hull import build_sphere_from_points
+        times = []
+        for i in range(warmup + steps):
+            t = time.perf_counter()
+            build_sphere_from_points(xyz)
+            if i >= warmup:
+                times.append(time.perf_counter() - t)
+        return times, {"mesh_s": times[-1]}
     pre = hot = eroded = None
     if workload in ("post", "climate"):
         pre, hot = elevation()
@@ -266,6 +289,8 @@ def algorithmic_bytes(name: str, N: int, E: int, land: int):
         "pb::k_flood_heap": 86 * land,
         # per filled cell: surface 4 + elev r/w 8 + depth 4 + path reads; tabulated per land cell as in SURVEY §8d (30·L)
         "pb::k_carve_lift": 30 * land,
+        # sorted f64 coordinates 24 + key 4 + id 4 + degree/offset 4 + row written 4·6 (candidates assumed cached)
+        "pb::StarK": 60 * N,
         "pb::SmoothFieldK": csr + 8 * N,
         "pb::SmoothMaskedK": csr + 9 * N,
         "pb::DiffuseWarmthK": csr + 12 * N,
@@ -302,12 +327,16 @@ def run_b200(args):
 
     wl = args.workload
     do_elev, do_post, do_clim = wl in ("full", "elevation"), wl in ("full", "post"), wl in ("full", "climate")
+    do_mesh = wl in ("full", "mesh")
     # replicas: every rank processes its own copy of the same seeded planet (identical work per GPU, so the
     # N-GPU numbers are a clean weak-scaling series)
-    inp = Inputs(args.cells, SEED)
+    inp = Inputs(args.cells, SEED, on_device=local)
     mesh, xyz = inp.mesh, inp.xyz
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
     dm = DeviceMesh(mesh, xyz, device=local)
+    xyz_t = torch.from_numpy(xyz).to(dev)
+    off_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    adj_t = torch.empty(E, dtype=torch.int32, device=dev)
     if args.flood:
         dm.set_option("flood", args.flood)
 
@@ -332,11 +361,15 @@ def run_b200(args):
     elevation_device()
     pre = state["elev"].clone()
     land = int((pre > 0).sum().item())
+    if wl == "mesh":
+        state["elev"] = pre
     if wl == "climate":
         post_device()
 
     def step_device():
         flush.zero_()
+        if do_mesh:
+            dm.triangulateSphere(xyz_t, off_t, adj_t)
         if do_elev:
             elevation_device()
         elif do_post:
@@ -397,7 +430,15 @@ def run_b200(args):
 
     # ---- end to end through the host-pointer C ABI ------------------------------------------------
     elev_dev_final = state["elev"].clone()
+    mesh_same = True
+    if do_mesh:   # the adjacency rebuilt inside the timed steps is the one the mesh was created from
+        mesh_same = bool((off_t.cpu() == torch.from_numpy(mesh.adjOffset)).all().item()) and \
+            bool((adj_t.cpu() == torch.from_numpy(mesh.adjList)).all().item())
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_xyz = pin(xyz)
+    h_off = torch.empty(N + 1, dtype=torch.int32).pin_memory()
+    h_adj = torch.empty(E, dtype=torch.int32).pin_memory()
+    np_xyz, np_off, np_adj = h_xyz.numpy(), h_off.numpy(), h_adj.numpy()
     h_plate, h_super, h_pre, h_hot0 = pin(inp.r_plate), pin(inp.r_super), pin(pre.cpu().numpy()), pin(state["hotspot"].cpu().numpy())
     h_elev = torch.empty(N, dtype=torch.float32).pin_memory()
     h_delta = torch.empty(N, dtype=torch.float32).pin_memory()
@@ -406,30 +447,41 @@ def run_b200(args):
     np_delta, np_ocean, np_koppen, np_plate, np_super = h_delta.numpy(), h_ocean.numpy(), h_koppen.numpy(), h_plate.numpy(), h_super.numpy()
     if wl == "climate":
         h_elev.copy_(elev_dev_final.cpu())
-    h2d = (8 * N if do_elev else 0) + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
-    d2h = ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
+    h2d = (12 * N if do_mesh else 0) + (8 * N if do_elev else 0) + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
+    d2h = (4 * (N + 1) + 4 * E if do_mesh else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
           ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
     reply, host = {}, {}
+
+    host_stage = {}
 
     def step_host():
         flush.zero_()
         np_elev, np_hot = h_elev.numpy(), h_hot0.numpy()
+        tt = [time.perf_counter()]
+        if do_mesh:
+            dm.triangulateSphere(np_xyz, np_off, np_adj)
+        tt.append(time.perf_counter())
         if do_elev:
             res = assignElevation(dm, None, inp.pio, np_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
                                   inp.super_data(np_super))
             np_elev, np_hot = res["r_elevation"], res["debugLayers"]["hotspot"]
         elif do_post:
             h_elev.copy_(h_pre)
+        tt.append(time.perf_counter())
         if do_post:
             runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, np_hot, hItersOverride=args.hiters,
                               out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
+        tt.append(time.perf_counter())
         if do_clim:
             w, o, p, t, _ = cl.computeClimate(dm, np_elev, inp.pio, np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
             for res, keys in ((w, CLIMATE_REPLY_F32[:4] + ["itczLons", "itczLatsSummer", "itczLatsWinter"]),
                               (o, CLIMATE_REPLY_F32[4:12]), (p, CLIMATE_REPLY_F32[12:14]), (t, CLIMATE_REPLY_F32[14:])):
                 for k in keys:
                     reply[k] = res[k]     # device → host copy of every array of the climateDone message
+        tt.append(time.perf_counter())
         host["elev"] = np_elev
+        host_stage.update(mesh_ms=1e3 * (tt[1] - tt[0]), elevation_ms=1e3 * (tt[2] - tt[1]), post_ms=1e3 * (tt[3] - tt[2]),
+                          climate_ms=1e3 * (tt[4] - tt[3]))
 
     step_host()
     barrier()
@@ -444,8 +496,9 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = N * world * args.steps / e2e_s
     # host-pointer and device-pointer passes agree bit for bit
-    same = bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item()) and \
-        (not do_clim or bool((h_koppen == koppen.cpu()).all().item()))
+    same = (wl == "mesh" or bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item())) and \
+        (not do_clim or bool((h_koppen == koppen.cpu()).all().item())) and mesh_same and \
+        (not do_mesh or (bool((h_off == torch.from_numpy(mesh.adjOffset)).all().item()) and bool((h_adj == torch.from_numpy(mesh.adjList)).all().item())))
 
     # ---- roofline (events recorded inside the timed region) ---------------------------------------------
     peaks = {}
@@ -478,7 +531,10 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         times, stages = oracle_step_seconds(inp, args.hiters, 1, 0, wl)
         cpu_baseline = {"value": N / times[0], "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread",
+                        "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread"
+                                  + ("; mesh construction is not in the CPU figure (its checker is qhull, not the reference's "
+                                     "Delaunator: `--workload mesh` times it separately)" if wl == "full" else
+                                     " (qhull convex hull + SphereMesh constructor, scipy)" if wl == "mesh" else ""),
                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages": stages}
 
     if rank == 0:
@@ -491,11 +547,12 @@ def run_b200(args):
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
                        "flood": args.flood or "device",
-                       "inputs": "mesh and plate tables are seeded synthetic stand-ins for the upstream stages (mesh "
-                                 "construction, plate pipeline), resident before the timed region"},
+                       "inputs": "points (seeded jittered Fibonacci sphere) and plate tables (seeded synthetic stand-ins for "
+                                 "the plate pipeline) are resident before the timed region; the mesh adjacency is "
+                                 "rebuilt from the points inside every step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
-                    "matches_device_path": same},
+                    "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
             "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "library": dm.lib.version,
         }), flush=True)
@@ -523,7 +580,7 @@ def run_sharded_sweeps(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    mesh, xyz = get_planet(args.cells)
+    mesh, xyz = get_planet(args.cells, on_device=local)
     N = mesh.numRegions
     field0 = synthetic_elevation(xyz, SEED, 0.3)
     sh = Shard(mesh, xyz, world, rank)
@@ -595,7 +652,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "sharded-sweeps"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "mesh", "sharded-sweeps"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],

@@ -209,6 +209,20 @@ pb_status pb_compute_climate(pb_climate* climate, const float* r_elevation, cons
 pb_status pb_climate_field_info(pb_climate* climate, const char* name, int32_t* kind_out, int64_t* count_out);
 pb_status pb_climate_get(pb_climate* climate, const char* name, void* out);
 
+/* ---- mesh construction ------------------------------------------------------------------
+ * pb_triangulate_sphere replaces the triangulation inside buildSphere and the SphereMesh constructor's adjacency
+ * (js/sphere-mesh.js:94-146, 174-186; Delaunator 5.0.1 + addPoleToMesh): r_xyz holds numRegions unit vectors (the
+ * pole vertex (0,0,1) included as the reference does, :179-183); adjOffset[numRegions+1] and adjList[6*numRegions-12]
+ * receive the CSR neighbour lists of the spherical Delaunay triangulation (= convex hull), each row in the
+ * reference's circulation order `s = next(halfedges[s])` for the canonical triangle numbering described in
+ * csrc/pb_meshgen.h.  Arrays follow the context's pointer mode.  PB_ERR_INVALID when the points do not give a closed
+ * triangulated sphere (duplicates, fewer than 4 points).
+ * pb_mesh_create_from_points = pb_triangulate_sphere + pb_mesh_create without the round trip through the host;
+ * pb_mesh_get_adjacency returns the CSR arrays of a mesh (host pointers). */
+pb_status pb_triangulate_sphere(pb_context* ctx, int32_t numRegions, const float* r_xyz, int32_t* adjOffset, int32_t* adjList);
+pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
+pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* adjOffset, int32_t* adjList);
+
 /* ---- cell-range shards with device-side halo exchange (no reference counterpart: the reference is one thread) ----
  * One process per GPU.  `mesh` is the rank's LOCAL mesh: owned cells [0, nOwn) followed by the halo cells its rows
  * read (halo rows empty), see planet_heightmap_generation_b200/sharded.py.  For every peer the caller gives the

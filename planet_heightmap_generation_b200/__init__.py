@@ -2,4 +2,4 @@
 (raguilar011095/planet_heightmap_generation).  See DESIGN.md."""
 from ._lib import Library, PlanetB200Error, default_library  # noqa: F401
 from .engine import DeviceMesh  # noqa: F401
-from .mesh import SphereMesh, build_sphere_from_points  # noqa: F401
+from .mesh import SphereMesh  # noqa: F401

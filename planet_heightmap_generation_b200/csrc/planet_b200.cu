@@ -5,6 +5,7 @@
 #include "pb_climate_engine.h"
 #include "pb_elevation_engine.h"
 #include "pb_shard.h"
+#include "pb_meshgen.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -32,7 +33,12 @@ void need(bool c, const char* what) {
 }
 }  // namespace
 
-struct pb_context { pb::Context c; explicit pb_context(int d) : c(d) {} };
+struct pb_context {
+    pb::Context c;
+    std::unique_ptr<pb::SphereTriangulator> tri;   // scratch of pb_triangulate_sphere, kept between calls
+    pb::DevBuf<float> triXyz; pb::DevBuf<int> triOff, triAdj;
+    explicit pb_context(int d) : c(d) {}
+};
 struct pb_mesh {
     pb::Mesh m;
     std::unique_ptr<pb::Elevation> elevation;
@@ -395,6 +401,48 @@ pb_status pb_climate_get(pb_climate* climate, const char* name, void* out) {
         const void* src = k == 0 ? (const void*)c.cF(name) : k == 1 ? (const void*)c.cI(name) : (const void*)c.cU(name);
         pb::dev_copy(out, src, it->second * (k == 2 ? 1 : 4), m.hostMode() ? 1 : 2, m.ex().stream);
         m.finish();
+    });
+}
+
+// ---- mesh construction ------------------------------------------------------------------------------------------
+static void triangulate(pb_context* ctx, int n, const float* xyz, bool hostPtrs, std::vector<int>* hOff, std::vector<int>* hAdj,
+                        int32_t* outOff, int32_t* outAdj) {
+    if (n < 4) throw std::invalid_argument("a sphere mesh needs at least 4 points");
+    const pb::Exec& ex = ctx->c.ex;
+    const size_t E = 6 * (size_t)n - 12;
+    pb::DevBuf<float>& dXyz = ctx->triXyz; pb::DevBuf<int>& dOff = ctx->triOff; pb::DevBuf<int>& dAdj = ctx->triAdj;
+    const float* px = xyz;
+    if (hostPtrs) { pb::dev_copy(dXyz.ensure(3 * (size_t)n), xyz, sizeof(float) * 3 * (size_t)n, 0, ex.stream); px = dXyz.p; }
+    int* po = (!hostPtrs && outOff) ? outOff : dOff.ensure((size_t)n + 1);
+    int* pa = (!hostPtrs && outAdj) ? outAdj : dAdj.ensure(E);
+    if (!ctx->tri) ctx->tri.reset(new pb::SphereTriangulator());
+    ctx->tri->build(ex, n, px, po, pa);
+    if (hostPtrs && outOff) { pb::dev_copy(outOff, po, sizeof(int) * ((size_t)n + 1), 1, ex.stream); pb::dev_copy(outAdj, pa, sizeof(int) * E, 1, ex.stream); }
+    if (hOff) { hOff->resize((size_t)n + 1); hAdj->resize(E);
+                pb::dev_copy(hOff->data(), po, sizeof(int) * ((size_t)n + 1), 1, ex.stream); pb::dev_copy(hAdj->data(), pa, sizeof(int) * E, 1, ex.stream); }
+    pb::stream_sync(ex.stream);
+}
+pb_status pb_triangulate_sphere(pb_context* ctx, int32_t n, const float* xyz, int32_t* off, int32_t* adj) {
+    return guard([&] {
+        need(ctx && xyz && off && adj, "NULL argument");
+        ctx->c.bind();
+        triangulate(ctx, n, xyz, ctx->c.pointerMode == PB_POINTER_HOST, nullptr, nullptr, off, adj);
+    });
+}
+pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t n, const float* xyz, pb_mesh** out) {
+    return guard([&] {
+        need(ctx && xyz && out, "NULL argument");
+        ctx->c.bind();
+        std::vector<int> hOff, hAdj;
+        triangulate(ctx, n, xyz, true, &hOff, &hAdj, nullptr, nullptr);
+        *out = new pb_mesh(&ctx->c, n, hOff.data(), hAdj.data(), xyz);
+    });
+}
+pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* off, int32_t* adj) {
+    return guard([&] {
+        need(mesh && off && adj, "NULL argument");
+        memcpy(off, mesh->m.hOffCopy.data(), sizeof(int) * mesh->m.hOffCopy.size());
+        memcpy(adj, mesh->m.hAdjCopy.data(), sizeof(int) * mesh->m.hAdjCopy.size());
     });
 }
 

@@ -44,6 +44,27 @@ class DeviceMesh:
                                         self.adjList.ctypes.data, self.r_xyz.ctypes.data, C.byref(self._mesh)))
         self._mode = _lib.POINTER_HOST
 
+    @classmethod
+    def from_points(cls, r_xyz, device: int = 0, lib: Library | None = None) -> "DeviceMesh":
+        """buildSphere's triangulation on the device (js/sphere-mesh.js:174-186 → csrc/pb_meshgen.h): r_xyz holds the
+        unit vectors of all regions, pole vertex included; adjOffset / adjList come back from the GPU."""
+        self = cls.__new__(cls)
+        self.lib = lib or default_library()
+        self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
+        self.numRegions = self.r_xyz.shape[0] // 3
+        self.device = device
+        self._ctx = C.c_void_p()
+        self._mesh = C.c_void_p()
+        d = self.lib.dll
+        self.lib.check(d.pb_context_create(device, C.byref(self._ctx)))
+        self.lib.check(d.pb_mesh_create_from_points(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
+        self.numEdges = int(d.pb_mesh_num_edges(self._mesh))
+        self.adjOffset = np.empty(self.numRegions + 1, np.int32)
+        self.adjList = np.empty(self.numEdges, np.int32)
+        self.lib.check(d.pb_mesh_get_adjacency(self._mesh, self.adjOffset.ctypes.data, self.adjList.ctypes.data))
+        self._mode = _lib.POINTER_HOST
+        return self
+
     def close(self):
         if getattr(self, "_mesh", None):
             self.lib.dll.pb_mesh_destroy(self._mesh)
@@ -117,6 +138,23 @@ class DeviceMesh:
         return int(self.lib.dll.pb_launch_count())
 
     # ---- mesh primitives ------------------------------------------------------------------------------
+    def triangulateSphere(self, r_xyz, adjOffset=None, adjList=None):
+        """Spherical Delaunay adjacency of `r_xyz` (buildSphere's triangulation + the SphereMesh constructor,
+        js/sphere-mesh.js:94-146, 174-186) on this context's GPU.  numpy in → numpy out, torch.cuda in → torch.cuda out."""
+        n = int(r_xyz.shape[0] if r_xyz.ndim == 1 else r_xyz.shape[0] * r_xyz.shape[1]) // 3
+        if adjOffset is None:
+            if _is_torch_cuda(r_xyz):
+                import torch
+                adjOffset = torch.empty(n + 1, dtype=torch.int32, device=r_xyz.device)
+                adjList = torch.empty(6 * n - 12, dtype=torch.int32, device=r_xyz.device)
+            else:
+                adjOffset, adjList = np.empty(n + 1, np.int32), np.empty(6 * n - 12, np.int32)
+        self._begin(r_xyz, adjOffset, adjList)
+        self.lib.check(self.lib.dll.pb_triangulate_sphere(
+            self._ctx, n, self._ptr(r_xyz, "f32", 3 * n, "r_xyz"), self._ptr(adjOffset, "i32", n + 1, "adjOffset"),
+            self._ptr(adjList, "i32", 6 * n - 12, "adjList")))
+        return adjOffset, adjList
+
     def computeNeighborDist(self, out=None):
         """js/sphere-mesh.js:191-203"""
         if out is None:

@@ -1,7 +1,7 @@
 """Host-side generators for synthetic seeded planets (inputs of the hot path, not part of it).
 
 `fibonacci_sphere` follows js/sphere-mesh.js:9-37 (generateFibonacciSphere with makeRng jitter) in
-vectorised numpy; `build_sphere` adds the pole vertex and triangulates (mesh.py).  numpy's
+vectorised numpy; `build_sphere` adds the pole vertex and triangulates on the device.  numpy's
 sin/cos/asin may differ from V8's in the last ulp of a double, which can flip an f32 store for a
 handful of points — irrelevant here because the same r_xyz array is handed to every implementation
 being compared.
@@ -10,7 +10,6 @@ from __future__ import annotations
 
 import numpy as np
 
-from .mesh import build_sphere_from_points
 
 _M = 2147483647
 
@@ -62,12 +61,21 @@ def fibonacci_sphere(N: int, jitter: float, seed: float) -> np.ndarray:
     return out.reshape(-1)
 
 
-def build_sphere(N: int, jitter: float, seed: float):
-    """buildSphere (js/sphere-mesh.js:174-186): N Fibonacci points + the pole vertex (0,0,1) as id N."""
+def sphere_points(N: int, jitter: float, seed: float) -> np.ndarray:
+    """N Fibonacci points + the pole vertex (0,0,1) as id N (js/sphere-mesh.js:175, 179-183)."""
     xyz = np.empty(3 * (N + 1), np.float32)
     xyz[:3 * N] = fibonacci_sphere(N, jitter, seed)
     xyz[3 * N:] = (0, 0, 1)
-    return build_sphere_from_points(xyz)
+    return xyz
+
+
+def build_sphere(N: int, jitter: float, seed: float, device: int = 0, lib=None):
+    """buildSphere (js/sphere-mesh.js:174-186) → {mesh, r_xyz}: the triangulation runs on the GPU
+    (csrc/pb_meshgen.h) and the returned DeviceMesh carries adjOffset / adjList like the reference's mesh."""
+    from .engine import DeviceMesh
+    xyz = sphere_points(N, jitter, seed)
+    dm = DeviceMesh.from_points(xyz, device=device, lib=lib)
+    return {"mesh": dm, "r_xyz": dm.r_xyz}
 
 
 def synthetic_elevation(r_xyz: np.ndarray, seed: int, land_fraction: float = 0.3) -> np.ndarray:

@@ -62,7 +62,7 @@ def make_planet(oracle, n_cells, seed=42, land=0.3):
     """(SphereMesh, r_xyz, neighborDist, synthetic elevation) — cached per size."""
     key = (n_cells, seed, land)
     if key not in _planet_cache:
-        from planet_heightmap_generation_b200.mesh import build_sphere_from_points
+        from oracle.mesh_hull import build_sphere_from_points
         from planet_heightmap_generation_b200.sphere import synthetic_elevation
         xyz = oracle.fibonacci_sphere(n_cells, 0.75, seed)
         mesh, xyz = build_sphere_from_points(xyz)

@@ -24,7 +24,7 @@ def sha(a):
 
 def compute():
     from oracle import binding as oracle
-    from planet_heightmap_generation_b200.mesh import build_sphere_from_points
+    from oracle.mesh_hull import build_sphere_from_points
     from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plate_tables
     xyz = oracle.fibonacci_sphere(3000, 0.75, 42)
     mesh, xyz = build_sphere_from_points(xyz)

@@ -1,0 +1,100 @@
+"""Mesh construction on the device: pb_triangulate_sphere / pb_mesh_create_from_points against
+the CPU checker oracle/mesh_hull.py (qhull convex hull + the SphereMesh constructor's circulation), bit-exact CSR."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from planet_heightmap_generation_b200 import _lib
+from planet_heightmap_generation_b200.engine import DeviceMesh
+from planet_heightmap_generation_b200.sphere import sphere_points
+
+
+def _hull(xyz):
+    from oracle.mesh_hull import build_sphere_from_points
+    return build_sphere_from_points(xyz)
+
+
+def _check_same(dm, mesh):
+    assert np.array_equal(dm.adjOffset, mesh.adjOffset)
+    assert np.array_equal(dm.adjList, mesh.adjList)
+
+
+@pytest.mark.parametrize("n,seed", [(30, 3.0), (500, 11.0), (3000, 42.0), (20000, 7.0)])
+def test_fibonacci_sphere_matches_hull(backend, n, seed):
+    xyz = sphere_points(n, 0.75, seed)
+    mesh, xyz = _hull(xyz)
+    dm = DeviceMesh.from_points(xyz, lib=backend)
+    _check_same(dm, mesh)
+    assert dm.numEdges == 6 * (n + 1) - 12
+    dm.close()
+
+
+def test_irregular_point_sets_match_hull(backend):
+    """Uniform random points and a dense cluster: the grid block has to grow for some stars."""
+    rng = np.random.default_rng(5)
+    p = rng.normal(size=(20000, 3))
+    p /= np.linalg.norm(p, axis=1, keepdims=True)
+    q = rng.normal(size=(4000, 3)) * 0.05 + np.array([0.3, 0.4, 0.85])
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    for pts in (p, np.concatenate([p[:4000], q])):
+        mesh, xyz = _hull(pts.astype(np.float32).reshape(-1))
+        dm = DeviceMesh.from_points(xyz, lib=backend)
+        _check_same(dm, mesh)
+        dm.close()
+
+
+def test_mesh_from_points_runs_the_hot_path(backend, oracle):
+    """A mesh built on the device is an ordinary pb_mesh: smoothField over it equals the oracle on the hull mesh."""
+    from planet_heightmap_generation_b200.climate_util import smoothField
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation
+    xyz = sphere_points(3000, 0.75, 42.0)
+    mesh, xyz = _hull(xyz)
+    dm = DeviceMesh.from_points(xyz, lib=backend)
+    f = synthetic_elevation(xyz, 42, 0.3)
+    want = f.copy()
+    oracle.smooth_field(mesh, want, 3)
+    smoothField(dm, f, 3)
+    assert (f.view(np.uint32) == want.view(np.uint32)).all()
+    nd = dm.computeNeighborDist()
+    assert (nd.view(np.uint32) == oracle.neighbor_dist(mesh, xyz).view(np.uint32)).all()
+    dm.close()
+
+
+def test_triangulate_sphere_entry_and_errors(backend):
+    lib = backend
+    ctx = C.c_void_p()
+    lib.check(lib.dll.pb_context_create(0, C.byref(ctx)))
+    xyz = sphere_points(2000, 0.75, 1.0)
+    n = xyz.size // 3
+    off = np.empty(n + 1, np.int32)
+    adj = np.empty(6 * n - 12, np.int32)
+    lib.check(lib.dll.pb_triangulate_sphere(ctx, n, xyz.ctypes.data, off.ctypes.data, adj.ctypes.data))
+    mesh, _ = _hull(xyz)
+    assert np.array_equal(off, mesh.adjOffset) and np.array_equal(adj, mesh.adjList)
+    # duplicate points cannot form a closed triangulation
+    bad = xyz.copy()
+    bad[3:6] = bad[0:3]
+    rc = lib.dll.pb_triangulate_sphere(ctx, n, bad.ctypes.data, off.ctypes.data, adj.ctypes.data)
+    assert rc != 0 and b"Delaunay" in lib.dll.pb_last_error()
+    rc = lib.dll.pb_triangulate_sphere(ctx, 3, xyz.ctypes.data, off.ctypes.data, adj.ctypes.data)
+    assert rc != 0
+    lib.dll.pb_context_destroy(ctx)
+
+
+@pytest.mark.gpu
+def test_million_cell_mesh_on_device(cuda_lib):
+    """1M cells: closed triangulated sphere (Euler), symmetric, and identical to the hull checker."""
+    xyz = sphere_points(1_000_000, 0.75, 42.0)
+    dm = DeviceMesh.from_points(xyz, lib=cuda_lib)
+    n = dm.numRegions
+    assert dm.numEdges == 6 * n - 12
+    deg = np.diff(dm.adjOffset)
+    assert deg.min() >= 3 and deg.max() <= 32
+    src = np.repeat(np.arange(n, dtype=np.int64), deg)
+    fwd = np.sort(src * n + dm.adjList)
+    rev = np.sort(dm.adjList.astype(np.int64) * n + src)
+    assert np.array_equal(fwd, rev)
+    mesh, _ = _hull(xyz)
+    _check_same(dm, mesh)
+    dm.close()
