@@ -57,15 +57,13 @@ def get_planet(cells: int, seed: int = SEED, on_device: int | None = None):
     """Mesh + r_xyz of the seeded planet.  Own arm (`on_device` = GPU index): triangulated on that GPU by the
     product path (DeviceMesh.from_points).  Reference arm: the CPU checker oracle/mesh_hull.py, cached on disk."""
     from planet_heightmap_generation_b200.mesh import SphereMesh
-    from planet_heightmap_generation_b200.sphere import fibonacci_sphere, sphere_points
     if on_device is not None:
         from planet_heightmap_generation_b200.engine import DeviceMesh
-        xyz = sphere_points(cells, 0.75, seed)
         t = time.time()
-        dm = DeviceMesh.from_points(xyz, device=on_device)
-        mesh = SphereMesh.from_csr(dm.adjOffset, dm.adjList)
+        dm = DeviceMesh.build_sphere(cells, 0.75, seed, device=on_device)
+        mesh, xyz = SphereMesh.from_csr(dm.adjOffset, dm.adjList), dm.r_xyz.copy()
         dm.close()
-        log(f"[bench] {cells}-cell mesh triangulated on the GPU in {time.time() - t:.2f}s (first call, includes context creation)")
+        log(f"[bench] {cells}-cell sphere generated and triangulated on the GPU in {time.time() - t:.2f}s (first call, includes context creation)")
         return mesh, xyz
     from oracle.mesh_hull import build_sphere_from_points
     cache_dir = os.path.join(tempfile.gettempdir(), "planet_b200_cache")
@@ -77,10 +75,9 @@ def get_planet(cells: int, seed: int = SEED, on_device: int | None = None):
         except Exception:
             pass
     t = time.time()
-    xyz = np.empty(3 * (cells + 1), np.float32)
-    xyz[:3 * cells] = fibonacci_sphere(cells, 0.75, seed)
-    xyz[3 * cells:] = (0, 0, 1)
-    mesh, xyz = build_sphere_from_points(xyz)
+    from oracle import binding as oracle
+    oracle.build()
+    mesh, xyz = build_sphere_from_points(oracle.fibonacci_sphere(cells, 0.75, seed))
     log(f"[bench] built {cells}-cell mesh in {time.time() - t:.1f}s")
     try:
         os.makedirs(cache_dir, exist_ok=True)
@@ -120,7 +117,7 @@ def workload_name(cells, hiters, workload):
     post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
             f"ridge 3, creep 3")
     clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
-    tri = "spherical Delaunay adjacency of the points (buildSphere's triangulation + SphereMesh constructor)"
+    tri = "buildSphere (Fibonacci points with seeded jitter + pole, spherical Delaunay adjacency in the SphereMesh constructor's order)"
     what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri,
             "full": tri + " then " + elev + " then " + post + " then " + clim}[workload]
     return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
@@ -208,7 +205,7 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
         times = []
         for i in range(warmup + steps):
             t = time.perf_counter()
-            build_sphere_from_points(xyz)
+            build_sphere_from_points(oracle.fibonacci_sphere(mesh.numRegions - 1, 0.75, SEED))
             if i >= warmup:
                 times.append(time.perf_counter() - t)
         return times, {"mesh_s": times[-1]}
@@ -334,7 +331,7 @@ def run_b200(args):
     mesh, xyz = inp.mesh, inp.xyz
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
     dm = DeviceMesh(mesh, xyz, device=local)
-    xyz_t = torch.from_numpy(xyz).to(dev)
+    xyz_t = torch.empty(3 * N, dtype=torch.float32, device=dev)
     off_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
     adj_t = torch.empty(E, dtype=torch.int32, device=dev)
     if args.flood:
@@ -369,6 +366,7 @@ def run_b200(args):
     def step_device():
         flush.zero_()
         if do_mesh:
+            dm.generateFibonacciSphere(args.cells, 0.75, SEED, out=xyz_t)
             dm.triangulateSphere(xyz_t, off_t, adj_t)
         if do_elev:
             elevation_device()
@@ -432,10 +430,11 @@ def run_b200(args):
     elev_dev_final = state["elev"].clone()
     mesh_same = True
     if do_mesh:   # the adjacency rebuilt inside the timed steps is the one the mesh was created from
-        mesh_same = bool((off_t.cpu() == torch.from_numpy(mesh.adjOffset)).all().item()) and \
+        mesh_same = bool((xyz_t.cpu() == torch.from_numpy(xyz)).all().item()) and \
+            bool((off_t.cpu() == torch.from_numpy(mesh.adjOffset)).all().item()) and \
             bool((adj_t.cpu() == torch.from_numpy(mesh.adjList)).all().item())
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_xyz = pin(xyz)
+    h_xyz = torch.empty(3 * N, dtype=torch.float32).pin_memory()
     h_off = torch.empty(N + 1, dtype=torch.int32).pin_memory()
     h_adj = torch.empty(E, dtype=torch.int32).pin_memory()
     np_xyz, np_off, np_adj = h_xyz.numpy(), h_off.numpy(), h_adj.numpy()
@@ -447,8 +446,8 @@ def run_b200(args):
     np_delta, np_ocean, np_koppen, np_plate, np_super = h_delta.numpy(), h_ocean.numpy(), h_koppen.numpy(), h_plate.numpy(), h_super.numpy()
     if wl == "climate":
         h_elev.copy_(elev_dev_final.cpu())
-    h2d = (12 * N if do_mesh else 0) + (8 * N if do_elev else 0) + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
-    d2h = (4 * (N + 1) + 4 * E if do_mesh else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
+    h2d = (12 * N if do_mesh else 0) + (8 * N if do_elev else 0)     # mesh: r_xyz goes host → device for the triangulation + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
+    d2h = (12 * N + 4 * (N + 1) + 4 * E if do_mesh else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
           ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
     reply, host = {}, {}
 
@@ -459,6 +458,7 @@ def run_b200(args):
         np_elev, np_hot = h_elev.numpy(), h_hot0.numpy()
         tt = [time.perf_counter()]
         if do_mesh:
+            dm.generateFibonacciSphere(args.cells, 0.75, SEED, out=np_xyz)
             dm.triangulateSphere(np_xyz, np_off, np_adj)
         tt.append(time.perf_counter())
         if do_elev:
@@ -498,7 +498,8 @@ def run_b200(args):
     # host-pointer and device-pointer passes agree bit for bit
     same = (wl == "mesh" or bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item())) and \
         (not do_clim or bool((h_koppen == koppen.cpu()).all().item())) and mesh_same and \
-        (not do_mesh or (bool((h_off == torch.from_numpy(mesh.adjOffset)).all().item()) and bool((h_adj == torch.from_numpy(mesh.adjList)).all().item())))
+        (not do_mesh or (bool((h_xyz == torch.from_numpy(xyz)).all().item()) and
+                         bool((h_off == torch.from_numpy(mesh.adjOffset)).all().item()) and bool((h_adj == torch.from_numpy(mesh.adjList)).all().item())))
 
     # ---- roofline (events recorded inside the timed region) ---------------------------------------------
     peaks = {}
@@ -547,9 +548,8 @@ def run_b200(args):
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
                        "flood": args.flood or "device",
-                       "inputs": "points (seeded jittered Fibonacci sphere) and plate tables (seeded synthetic stand-ins for "
-                                 "the plate pipeline) are resident before the timed region; the mesh adjacency is "
-                                 "rebuilt from the points inside every step"},
+                       "inputs": "plate tables (seeded synthetic stand-ins for the plate pipeline) are resident before the "
+                                 "timed region; points and mesh adjacency are rebuilt from (N, jitter, seed) inside every step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},

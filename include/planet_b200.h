@@ -218,7 +218,11 @@ pb_status pb_climate_get(pb_climate* climate, const char* name, void* out);
  * csrc/pb_meshgen.h.  Arrays follow the context's pointer mode.  PB_ERR_INVALID when the points do not give a closed
  * triangulated sphere (duplicates, fewer than 4 points).
  * pb_mesh_create_from_points = pb_triangulate_sphere + pb_mesh_create without the round trip through the host;
- * pb_mesh_get_adjacency returns the CSR arrays of a mesh (host pointers). */
+ * pb_mesh_get_adjacency returns the CSR arrays of a mesh (host pointers).
+ * pb_generate_fibonacci_sphere replaces generateFibonacciSphere (js/sphere-mesh.js:9-37, jitter draws from
+ * makeRng(seed), js/rng.js:3-6) and appends the pole vertex as buildSphere does (:179-183): xyz receives
+ * 3*(numPoints+1) floats. */
+pb_status pb_generate_fibonacci_sphere(pb_context* ctx, int32_t numPoints, double jitter, double seed, float* r_xyz);
 pb_status pb_triangulate_sphere(pb_context* ctx, int32_t numRegions, const float* r_xyz, int32_t* adjOffset, int32_t* adjList);
 pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
 pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* adjOffset, int32_t* adjList);

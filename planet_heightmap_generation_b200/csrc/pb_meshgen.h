@@ -265,6 +265,58 @@ struct MeshGenSymmetryK {
     }
 };
 
+// generateFibonacciSphere (js/sphere-mesh.js:9-37) + the pole vertex buildSphere appends (:179-183).  z and lng are the
+// reference's running sums (z -= dz, lng += dlong: every step is rounded, so they are accumulated serially on the
+// host); the four jitter draws of point k are Park–Miller outputs 4k+1 … 4k+4 (js/rng.js:3-6), reached by jump-ahead:
+// state_m = s0 · 16807^m mod (2^31 - 1).
+struct FibonacciK {
+    int N; double jitter, s, dz; const double* z; const double* lng; unsigned long long s0; float* xyz;
+    static PB_DEV unsigned long long mulmod(unsigned long long a, unsigned long long b) { return (a * b) % 2147483647ull; }
+    PB_DEV void operator()(int k) const {
+        if (k == N) { xyz[3 * k] = 0.0f; xyz[3 * k + 1] = 0.0f; xyz[3 * k + 2] = 1.0f; return; }
+        const double zz = z[k];
+        const double r = sqrt(1 - zz * zz);
+        double latDeg = pb_asin(zz) * 180 / PB_PI;
+        double lonDeg = lng[k] * 180 / PB_PI;
+        if (jitter > 0) {
+            unsigned long long st = s0, base = 16807ull, e = 4ull * (unsigned long long)k;
+            while (e) { if (e & 1ull) st = mulmod(st, base); base = mulmod(base, base); e >>= 1; }
+            double u[4];
+            for (int i = 0; i < 4; i++) { st = mulmod(st, 16807ull); u[i] = (double)(st - 1ull) / 2147483646.0; }
+            const double jLat = u[0] - u[1], jLon = u[2] - u[3];
+            double nextZ = zz - dz * 2 * PB_PI * r / s;
+            if (nextZ < -1) nextZ = -1;
+            latDeg += jitter * jLat * (latDeg - pb_asin(nextZ) * 180 / PB_PI);
+            lonDeg += jitter * jLon * (s / r * 180 / PB_PI);
+        }
+        const double latR = latDeg * PB_PI / 180, lonR = lonDeg * PB_PI / 180;
+        xyz[3 * k] = (float)(pb_cos(latR) * pb_cos(lonR));
+        xyz[3 * k + 1] = (float)(pb_cos(latR) * pb_sin(lonR));
+        xyz[3 * k + 2] = (float)pb_sin(latR);
+    }
+};
+
+struct FibonacciSphere {
+    DevBuf<double> z, lng;
+    std::vector<double> hz, hlng;
+    int cachedN = 0;
+    // dXyz: device f32[3(N+1)]
+    void generate(const Exec& ex, int N, double jitter, double seed, float* dXyz) {
+        if (N < 1) throw Error("numPoints must be positive");
+        const double dz = 2.0 / N, dlong = PB_PI * (3 - sqrt(5.0));
+        if (cachedN != N) {                      // the two running sums depend on N only
+            hz.resize(N); hlng.resize(N);
+            double l = 0, zz = 1 - dz / 2;
+            for (int k = 0; k < N; k++, zz -= dz) { hz[k] = zz; hlng[k] = l; l += dlong; }
+            dev_copy(z.ensure(N), hz.data(), sizeof(double) * (size_t)N, 0, ex.stream);
+            dev_copy(lng.ensure(N), hlng.data(), sizeof(double) * (size_t)N, 0, ex.stream);
+            cachedN = N;
+        }
+        const unsigned long long s0 = (unsigned long long)(fmod(fabs(floor(seed * 9301.0 + 49297.0)), 2147483646.0) + 1.0);
+        ex.for_each(N + 1, FibonacciK{N, jitter, 3.6 / sqrt((double)N), dz, z.p, lng.p, s0, dXyz});
+    }
+};
+
 struct SphereTriangulator {
     DevBuf<uint32_t> key;
     DevBuf<int> sid, deg, fail, rows, pos;

@@ -37,6 +37,7 @@ struct pb_context {
     pb::Context c;
     std::unique_ptr<pb::SphereTriangulator> tri;   // scratch of pb_triangulate_sphere, kept between calls
     pb::DevBuf<float> triXyz; pb::DevBuf<int> triOff, triAdj;
+    std::unique_ptr<pb::FibonacciSphere> fib;
     explicit pb_context(int d) : c(d) {}
 };
 struct pb_mesh {
@@ -421,6 +422,23 @@ static void triangulate(pb_context* ctx, int n, const float* xyz, bool hostPtrs,
     if (hOff) { hOff->resize((size_t)n + 1); hAdj->resize(E);
                 pb::dev_copy(hOff->data(), po, sizeof(int) * ((size_t)n + 1), 1, ex.stream); pb::dev_copy(hAdj->data(), pa, sizeof(int) * E, 1, ex.stream); }
     pb::stream_sync(ex.stream);
+}
+pb_status pb_generate_fibonacci_sphere(pb_context* ctx, int32_t numPoints, double jitter, double seed, float* xyz) {
+    return guard([&] {
+        need(ctx && xyz, "NULL argument");
+        need(numPoints >= 1, "numPoints must be positive");
+        ctx->c.bind();
+        if (!ctx->fib) ctx->fib.reset(new pb::FibonacciSphere());
+        const pb::Exec& ex = ctx->c.ex;
+        const size_t n3 = 3 * ((size_t)numPoints + 1);
+        if (ctx->c.pointerMode == PB_POINTER_HOST) {
+            ctx->fib->generate(ex, numPoints, jitter, seed, ctx->triXyz.ensure(n3));
+            pb::dev_copy(xyz, ctx->triXyz.p, sizeof(float) * n3, 1, ex.stream);
+            pb::stream_sync(ex.stream);
+        } else {
+            ctx->fib->generate(ex, numPoints, jitter, seed, xyz);
+        }
+    });
 }
 pb_status pb_triangulate_sphere(pb_context* ctx, int32_t n, const float* xyz, int32_t* off, int32_t* adj) {
     return guard([&] {

@@ -50,13 +50,31 @@ class DeviceMesh:
         unit vectors of all regions, pole vertex included; adjOffset / adjList come back from the GPU."""
         self = cls.__new__(cls)
         self.lib = lib or default_library()
-        self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
-        self.numRegions = self.r_xyz.shape[0] // 3
         self.device = device
         self._ctx = C.c_void_p()
+        self._mesh = None
+        self.lib.check(self.lib.dll.pb_context_create(device, C.byref(self._ctx)))
+        return self._finish_from_points(r_xyz)
+
+    @classmethod
+    def build_sphere(cls, N: int, jitter: float, seed: float, device: int = 0, lib: Library | None = None) -> "DeviceMesh":
+        """buildSphere(N, jitter, rng) (js/sphere-mesh.js:174-186) entirely on the device: Fibonacci points with
+        makeRng(seed) jitter + the pole vertex, then the triangulation.  The result carries r_xyz, adjOffset, adjList."""
+        self = cls.__new__(cls)
+        self.lib = lib or default_library()
+        self.device = device
+        self._ctx = C.c_void_p()
+        self._mesh = None
+        self.lib.check(self.lib.dll.pb_context_create(device, C.byref(self._ctx)))
+        xyz = np.empty(3 * (int(N) + 1), np.float32)
+        self.lib.check(self.lib.dll.pb_generate_fibonacci_sphere(self._ctx, int(N), float(jitter), float(seed), xyz.ctypes.data))
+        return self._finish_from_points(xyz)
+
+    def _finish_from_points(self, r_xyz):
+        self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
+        self.numRegions = self.r_xyz.shape[0] // 3
         self._mesh = C.c_void_p()
         d = self.lib.dll
-        self.lib.check(d.pb_context_create(device, C.byref(self._ctx)))
         self.lib.check(d.pb_mesh_create_from_points(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
         self.numEdges = int(d.pb_mesh_num_edges(self._mesh))
         self.adjOffset = np.empty(self.numRegions + 1, np.int32)
@@ -138,6 +156,15 @@ class DeviceMesh:
         return int(self.lib.dll.pb_launch_count())
 
     # ---- mesh primitives ------------------------------------------------------------------------------
+    def generateFibonacciSphere(self, N: int, jitter: float, seed: float, out=None):
+        """generateFibonacciSphere + the pole vertex (js/sphere-mesh.js:9-37, 179-183): 3·(N+1) floats."""
+        if out is None:
+            out = np.empty(3 * (int(N) + 1), np.float32)
+        self._begin(out)
+        self.lib.check(self.lib.dll.pb_generate_fibonacci_sphere(self._ctx, int(N), C.c_double(jitter), C.c_double(seed),
+                                                                  self._ptr(out, "f32", 3 * (int(N) + 1), "out")))
+        return out
+
     def triangulateSphere(self, r_xyz, adjOffset=None, adjList=None):
         """Spherical Delaunay adjacency of `r_xyz` (buildSphere's triangulation + the SphereMesh constructor,
         js/sphere-mesh.js:94-146, 174-186) on this context's GPU.  numpy in → numpy out, torch.cuda in → torch.cuda out."""

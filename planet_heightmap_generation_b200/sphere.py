@@ -73,8 +73,7 @@ def build_sphere(N: int, jitter: float, seed: float, device: int = 0, lib=None):
     """buildSphere (js/sphere-mesh.js:174-186) → {mesh, r_xyz}: the triangulation runs on the GPU
     (csrc/pb_meshgen.h) and the returned DeviceMesh carries adjOffset / adjList like the reference's mesh."""
     from .engine import DeviceMesh
-    xyz = sphere_points(N, jitter, seed)
-    dm = DeviceMesh.from_points(xyz, device=device, lib=lib)
+    dm = DeviceMesh.build_sphere(N, jitter, seed, device=device, lib=lib)
     return {"mesh": dm, "r_xyz": dm.r_xyz}
 
 

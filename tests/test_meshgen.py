@@ -30,6 +30,30 @@ def test_fibonacci_sphere_matches_hull(backend, n, seed):
     dm.close()
 
 
+@pytest.mark.parametrize("n,jitter,seed", [(1, 0.75, 1.0), (1000, 0.0, 5.0), (3000, 0.75, 42.0), (20000, 0.75, 0.5), (70000, 1.0, 123456.0)])
+def test_fibonacci_points_match_oracle(backend, oracle, n, jitter, seed):
+    """generateFibonacciSphere on the device (jump-ahead Park–Miller, deterministic asin/sin/cos) vs the oracle's
+    sequential restatement: bit-exact, pole vertex appended."""
+    ctx = C.c_void_p()
+    backend.check(backend.dll.pb_context_create(0, C.byref(ctx)))
+    out = np.empty(3 * (n + 1), np.float32)
+    backend.check(backend.dll.pb_generate_fibonacci_sphere(ctx, n, C.c_double(jitter), C.c_double(seed), out.ctypes.data))
+    want = oracle.fibonacci_sphere(n, jitter, seed)
+    assert want.shape[0] == 3 * (n + 1) and tuple(want[-3:]) == (0.0, 0.0, 1.0)
+    assert (out.view(np.uint32) == want.view(np.uint32)).all()
+    backend.dll.pb_context_destroy(ctx)
+
+
+def test_build_sphere_on_device(backend, oracle):
+    """buildSphere = points + triangulation, both on the device; equals oracle points + hull checker."""
+    from planet_heightmap_generation_b200.sphere import build_sphere
+    got = build_sphere(5000, 0.75, 42.0, lib=backend)
+    mesh, xyz = _hull(oracle.fibonacci_sphere(5000, 0.75, 42.0))
+    assert (got["r_xyz"].view(np.uint32) == xyz.view(np.uint32)).all()
+    _check_same(got["mesh"], mesh)
+    got["mesh"].close()
+
+
 def test_irregular_point_sets_match_hull(backend):
     """Uniform random points and a dense cluster: the grid block has to grow for some stars."""
     rng = np.random.default_rng(5)
