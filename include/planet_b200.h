@@ -209,6 +209,32 @@ pb_status pb_compute_climate(pb_climate* climate, const float* r_elevation, cons
 pb_status pb_climate_field_info(pb_climate* climate, const char* name, int32_t* kind_out, int64_t* count_out);
 pb_status pb_climate_get(pb_climate* climate, const char* name, void* out);
 
+/* ---- plate pipeline on the hi-res mesh --------------------------------------------------
+ * pb_project_coarse_plates replaces projectCoarsePlates(mesh, r_xyz, coarseMesh, coarse_xyz, coarse_r_plate, seed,
+ * numPlates) (js/coarse-plates.js:51-117): the coarse mesh tables are host arrays (≈ 20 000 regions), numPlates < 0
+ * stands for `null`; r_plate[numRegions] (pointer mode) receives the plate seed id of every region.
+ * pb_smooth_and_reconnect_plates replaces smoothAndReconnectPlates(mesh, r_plate, plateSeeds, numPasses)
+ * (js/plates.js:241-348): r_plate is mutated in place; plateSeeds is a host array in Set order.
+ * pb_build_super_plates replaces buildSuperPlates(mesh, r_plate, plateSeeds, plateVec, plateIsOcean, plateDensity)
+ * (js/super-plates.js:16-273): `plates` lists the plates in plateSeeds order (pole[3k] = NaN: the plate has no
+ * plateVec entry; density = NaN: undefined); r_superPlate[numRegions] (pointer mode) and the caller-allocated
+ * super-plate table (capacity >= plates->n is always enough) receive the result; super plate ids are 0 … n-1. */
+typedef struct pb_super_plate_table {
+    int32_t capacity;        /* in: entries the arrays below can hold */
+    int32_t numSuperPlates;  /* out */
+    double* pole;            /* out: 3 per super plate */
+    double* omega;           /* out */
+    uint8_t* isOcean;        /* out */
+    double* density;         /* out */
+} pb_super_plate_table;
+pb_status pb_project_coarse_plates(pb_mesh* mesh, int32_t numCoarse, const int32_t* coarseAdjOffset, const int32_t* coarseAdjList,
+                                   const float* coarse_xyz, const int32_t* coarse_r_plate, double seed, int32_t numPlates,
+                                   int32_t* r_plate);
+pb_status pb_smooth_and_reconnect_plates(pb_mesh* mesh, int32_t* r_plate, const int32_t* plateSeeds, int32_t numSeeds,
+                                         int32_t numPasses);
+pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_plate_table* plates, int32_t* r_superPlate,
+                                pb_super_plate_table* superOut);
+
 /* ---- mesh construction ------------------------------------------------------------------
  * pb_triangulate_sphere replaces the triangulation inside buildSphere and the SphereMesh constructor's adjacency
  * (js/sphere-mesh.js:94-146, 174-186; Delaunator 5.0.1 + addPoleToMesh): r_xyz holds numRegions unit vectors (the

@@ -306,3 +306,51 @@ class Elevation:
 
 def pair_intensity(a, b):
     return lib().orc_pair_intensity(C.c_int(a), C.c_int(b))
+
+
+# ---- plate pipeline on the hi-res mesh (oracle/plates.cpp) --------------------------------------------------------
+def project_coarse_plates(mesh, xyz, coarse_mesh, coarse_xyz, coarse_r_plate, seed, num_plates=None):
+    """projectCoarsePlates (js/coarse-plates.js:51-117) → r_plate int32[N]."""
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    cxyz = np.ascontiguousarray(coarse_xyz, np.float32)
+    coff = np.ascontiguousarray(coarse_mesh.adjOffset, np.int32)
+    cadj = np.ascontiguousarray(coarse_mesh.adjList, np.int32)
+    crp = np.ascontiguousarray(coarse_r_plate, np.int32)
+    out = np.empty(mesh.numRegions, np.int32)
+    lib().orc_project_coarse_plates(C.c_int(mesh.numRegions), _p(xyz, C.c_float), C.c_int(coarse_mesh.numRegions),
+                                    _p(coff, C.c_int32), _p(cadj, C.c_int32), _p(cxyz, C.c_float), _p(crp, C.c_int32),
+                                    C.c_double(seed), C.c_int(-1 if num_plates is None else int(num_plates)), _p(out, C.c_int32))
+    return out
+
+
+def smooth_and_reconnect_plates(mesh, r_plate, plate_seeds, num_passes):
+    """smoothAndReconnectPlates (js/plates.js:241-348); r_plate mutated in place."""
+    seeds = np.ascontiguousarray(list(plate_seeds), np.int32)
+    lib().orc_smooth_and_reconnect_plates(*_mesh_args(mesh), _p(r_plate, C.c_int32), _p(seeds, C.c_int32),
+                                          C.c_int(seeds.size), C.c_int(num_passes))
+    return r_plate
+
+
+def build_super_plates(mesh, r_plate, plates):
+    """buildSuperPlates (js/super-plates.js:16-273).  plates: insertion-ordered dict pid → dict(isOcean, pole|None, omega,
+    density|None).  Returns (r_superPlate, dict sp → dict(isOcean, pole, omega, density))."""
+    r_plate = np.ascontiguousarray(r_plate, np.int32)
+    ids = np.ascontiguousarray(list(plates.keys()), np.int32)
+    has = np.ascontiguousarray([0 if plates[k].get("pole") is None else 1 for k in plates], np.uint8)
+    pole = np.ascontiguousarray([plates[k]["pole"] if plates[k].get("pole") is not None else (0, 0, 0) for k in plates], np.float64).reshape(-1)
+    om = np.ascontiguousarray([plates[k].get("omega", 0.0) for k in plates], np.float64)
+    oc = np.ascontiguousarray([1 if plates[k]["isOcean"] else 0 for k in plates], np.uint8)
+    de = np.ascontiguousarray([np.nan if plates[k].get("density") is None else plates[k]["density"] for k in plates], np.float64)
+    cap = max(ids.size, 2)
+    r_super = np.empty(mesh.numRegions, np.int32)
+    sp_pole, sp_om = np.zeros(3 * cap), np.zeros(cap)
+    sp_oc, sp_de = np.zeros(cap, np.uint8), np.zeros(cap)
+    n = lib().orc_build_super_plates(*_mesh_args(mesh), _p(r_plate, C.c_int32), C.c_int(ids.size), _p(ids, C.c_int32),
+                                     _p(has, C.c_uint8), _p(pole, C.c_double), _p(om, C.c_double), _p(oc, C.c_uint8),
+                                     _p(de, C.c_double), _p(r_super, C.c_int32), _p(sp_pole, C.c_double), _p(sp_om, C.c_double),
+                                     _p(sp_oc, C.c_uint8), _p(sp_de, C.c_double), C.c_int(cap))
+    if n < 0:
+        raise RuntimeError("super plate capacity")
+    table = {sp: dict(isOcean=bool(sp_oc[sp]), pole=tuple(sp_pole[3 * sp:3 * sp + 3]), omega=float(sp_om[sp]), density=float(sp_de[sp]))
+             for sp in range(n)}
+    return r_super, table

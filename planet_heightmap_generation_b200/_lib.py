@@ -66,6 +66,9 @@ SYMBOLS = {
     "pb_compute_climate": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _dbl, _dbl, _dbl, _dbl, _vp]),
     "pb_climate_field_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(_i32), C.POINTER(_i64)]),
     "pb_climate_get": (C.c_int, [_vp, C.c_char_p, _vp]),
+    "pb_project_coarse_plates": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, C.c_double, _i32, _vp]),
+    "pb_smooth_and_reconnect_plates": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
+    "pb_build_super_plates": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_generate_fibonacci_sphere": (C.c_int, [_vp, _i32, C.c_double, C.c_double, _vp]),
     "pb_triangulate_sphere": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "pb_mesh_create_from_points": (C.c_int, [_vp, _i32, _vp, C.POINTER(_vp)]),

@@ -6,6 +6,7 @@
 #include "pb_elevation_engine.h"
 #include "pb_shard.h"
 #include "pb_meshgen.h"
+#include "pb_plates.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -43,6 +44,8 @@ struct pb_context {
 struct pb_mesh {
     pb::Mesh m;
     std::unique_ptr<pb::Elevation> elevation;
+    std::unique_ptr<pb::Plates> plates;
+    pb::DevBuf<int> sPlateIO, sSuperIO;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
 
@@ -401,6 +404,56 @@ pb_status pb_climate_get(pb_climate* climate, const char* name, void* out) {
         const int k = c.kind[name];
         const void* src = k == 0 ? (const void*)c.cF(name) : k == 1 ? (const void*)c.cI(name) : (const void*)c.cU(name);
         pb::dev_copy(out, src, it->second * (k == 2 ? 1 : 4), m.hostMode() ? 1 : 2, m.ex().stream);
+        m.finish();
+    });
+}
+
+// ---- plate pipeline on the hi-res mesh -------------------------------------------------------------------------------
+static pb::Plates& plates_of(pb_mesh* mesh) {
+    if (!mesh->plates) mesh->plates.reset(new pb::Plates(&mesh->m));
+    return *mesh->plates;
+}
+pb_status pb_project_coarse_plates(pb_mesh* mesh, int32_t numCoarse, const int32_t* cOff, const int32_t* cAdj, const float* coarse_xyz,
+                                   const int32_t* coarse_r_plate, double seed, int32_t numPlates, int32_t* r_plate) {
+    return guard([&] {
+        need(mesh && cOff && cAdj && coarse_xyz && coarse_r_plate && r_plate, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        int* d = m.arg_out(r_plate, (size_t)m.N, mesh->sPlateIO);
+        plates_of(mesh).project(numCoarse, cOff, cAdj, coarse_xyz, coarse_r_plate, seed, numPlates, d);
+        m.arg_back(r_plate, d, (size_t)m.N);
+        m.finish();
+    });
+}
+pb_status pb_smooth_and_reconnect_plates(pb_mesh* mesh, int32_t* r_plate, const int32_t* plateSeeds, int32_t numSeeds, int32_t numPasses) {
+    return guard([&] {
+        need(mesh && r_plate && (plateSeeds || numSeeds == 0) && numSeeds >= 0 && numPasses >= 0, "bad argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        int* d = m.arg_in(r_plate, (size_t)m.N, mesh->sPlateIO);
+        plates_of(mesh).smooth_and_reconnect(d, plateSeeds, numSeeds, numPasses);
+        m.arg_back(r_plate, d, (size_t)m.N);
+        m.finish();
+    });
+}
+pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_plate_table* plates, int32_t* r_superPlate,
+                                pb_super_plate_table* superOut) {
+    return guard([&] {
+        need(mesh && r_plate && plates && r_superPlate && superOut, "NULL argument");
+        need(plates->n > 0 && plates->ids && plates->isOcean && plates->pole && plates->omega && plates->density, "incomplete plate table");
+        need(superOut->capacity >= 0 && superOut->pole && superOut->omega && superOut->isOcean && superOut->density, "incomplete output table");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        const int* dPlate = m.arg_in(r_plate, (size_t)m.N, mesh->sPlateIO);
+        int* dSuper = m.arg_out(r_superPlate, (size_t)m.N, mesh->sSuperIO);
+        pb::PlateTableIn T;
+        T.n = plates->n; T.ids = plates->ids; T.isOcean = plates->isOcean; T.pole = plates->pole; T.omega = plates->omega; T.density = plates->density;
+        pb::SuperPlatesOut o;
+        plates_of(mesh).build_super_plates(dPlate, T, dSuper, o);
+        if (o.n > superOut->capacity) throw std::invalid_argument("super-plate table capacity too small");
+        superOut->numSuperPlates = o.n;
+        for (int sp = 0; sp < o.n; sp++) {
+            for (int c = 0; c < 3; c++) superOut->pole[3 * sp + c] = o.pole[3 * sp + c];
+            superOut->omega[sp] = o.omega[sp]; superOut->isOcean[sp] = o.isOcean[sp]; superOut->density[sp] = o.density[sp];
+        }
+        m.arg_back(r_superPlate, dSuper, (size_t)m.N);
         m.finish();
     });
 }
