@@ -93,33 +93,34 @@ def get_planet(cells: int, seed: int = SEED, on_device: int | None = None):
 NMAG, SPREAD = 0.40, 5       # Roughness slider default (index.html) and the worker's fixed spread (planet-worker.js:138)
 
 
+NUM_PLATES, N_COARSE = 40, 20000
+
+
 class Inputs:
-    """What the hot path receives from the upstream stages (mesh construction, plate pipeline): mesh, r_xyz and
-    the plate tables — here seeded synthetic stand-ins (sphere.synthetic_plate_tables)."""
+    """What the path receives from the coarse stage (generateCoarsePlates, js/coarse-plates.js:19-39): the 20 000-region
+    coarse mesh of buildSphere(N_COARSE, 0.75, makeRng(seed + 137)) — built by the same device / checker code as the main
+    mesh — and a seeded synthetic plate assignment on it (sphere.synthetic_coarse_plates).  Everything downstream
+    (r_plate, super plates) is computed by the path itself."""
 
     def __init__(self, cells: int, seed: int = SEED, on_device: int | None = None):
-        from planet_heightmap_generation_b200.sphere import synthetic_elevation, synthetic_plate_tables
+        from planet_heightmap_generation_b200.sphere import synthetic_coarse_plates
         self.mesh, self.xyz = get_planet(cells, SEED, on_device)
-        hint = synthetic_elevation(self.xyz, seed, 0.3)       # only decides which plates are oceanic
-        self.r_plate, self.plates, self.seeds, self.r_super, self.super_plates = synthetic_plate_tables(self.xyz, hint, seed)
-        self.pio = {p for p, v in self.plates.items() if v["isOcean"]}
-        self.vec = {p: {"pole": v["pole"], "omega": v["omega"]} for p, v in self.plates.items()}
-        self.dens = {p: v["density"] for p, v in self.plates.items()}
-        sp = self.super_plates
-        self.super_data = lambda r_super: {
-            "r_superPlate": r_super, "superPlateIsOcean": {p for p, v in sp.items() if v["isOcean"]},
-            "superPlateVec": {p: {"pole": v["pole"], "omega": v["omega"]} for p, v in sp.items()},
-            "superPlateDensity": {p: v["density"] for p, v in sp.items()}}
+        self.cmesh, self.cxyz = get_planet(N_COARSE, SEED + 137, on_device)
+        self.crp, self.seeds, self.vec, self.pio, self.dens = synthetic_coarse_plates(self.cxyz, seed, NUM_PLATES)
+        # oracle-side plate table, plateSeeds order
+        self.plates = {s: dict(isOcean=s in self.pio, pole=tuple(self.vec[s]["pole"]), omega=self.vec[s]["omega"],
+                               density=self.dens[s]) for s in self.seeds}
 
 
 def workload_name(cells, hiters, workload):
-    elev = "assignElevation (40 plates, 10 super-plates, nMag 0.40, spread 5)"
+    elev = "assignElevation (nMag 0.40, spread 5, super plates on)"
     post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
             f"ridge 3, creep 3")
     clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
+    plat = f"projectCoarsePlates ({NUM_PLATES} plates on the {N_COARSE}-region coarse mesh) + smoothAndReconnectPlates(3) + buildSuperPlates"
     tri = "buildSphere (Fibonacci points with seeded jitter + pole, spherical Delaunay adjacency in the SphereMesh constructor's order)"
-    what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri,
-            "full": tri + " then " + elev + " then " + post + " then " + clim}[workload]
+    what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri, "plates": plat,
+            "full": " then ".join([tri, plat, elev, post, clim])}[workload]
     return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
 
 
@@ -196,9 +197,19 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
     oe = oracle.Elevation(mesh, xyz)
     clim = oracle.Climate(mesh, xyz)
 
+    pstate = {}
+
+    def plates():
+        rp = oracle.project_coarse_plates(mesh, xyz, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES)
+        oracle.smooth_and_reconnect_plates(mesh, rp, inp.seeds, 3)
+        rs, sp = oracle.build_super_plates(mesh, rp, inp.plates)
+        pstate.update(r_plate=rp, r_super=rs, super=sp)
+
     def elevation():
-        oe.assign(inp.r_plate, inp.plates, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.r_super, inp.super_plates)
+        oe.assign(pstate["r_plate"], inp.plates, inp.seeds, SEED, NMAG, SEED, SPREAD, pstate["r_super"], pstate["super"])
         return oe.get("r_elevation"), oe.get("hotspot")
+
+    plates()
 
     if workload == "mesh":
         from oracle.mesh_hull import build_sphere_from_points
@@ -219,6 +230,9 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
     for i in range(warmup + steps):
         t = time.perf_counter()
         e, h = (pre.copy(), hot) if pre is not None else (None, None)
+        if workload in ("full", "plates"):
+            plates()
+        t0 = time.perf_counter()
         if workload in ("full", "elevation"):
             e, h = elevation()
         t1 = time.perf_counter()
@@ -226,11 +240,11 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
             oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, h, hiters)
         t2 = time.perf_counter()
         if workload in ("full", "climate"):
-            clim.run_all(eroded if workload == "climate" else e, inp.pio, inp.r_plate, SEED)
+            clim.run_all(eroded if workload == "climate" else e, inp.pio, pstate["r_plate"], SEED)
         t3 = time.perf_counter()
         if i >= warmup:
             times.append(t3 - t)
-        stages = {"elevation_s": t1 - t, "post_s": t2 - t1, "climate_s": t3 - t2}
+        stages = {"plates_s": t0 - t, "elevation_s": t1 - t0, "post_s": t2 - t1, "climate_s": t3 - t2}
     return times, stages
 
 
@@ -307,6 +321,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from planet_heightmap_generation_b200 import climate as cl
+    from planet_heightmap_generation_b200 import plates as pl
     from planet_heightmap_generation_b200.elevation import DEBUG_LAYERS, assignElevation
     from planet_heightmap_generation_b200.engine import DeviceMesh
     from planet_heightmap_generation_b200.terrain_post import runPostProcessing
@@ -325,6 +340,7 @@ def run_b200(args):
     wl = args.workload
     do_elev, do_post, do_clim = wl in ("full", "elevation"), wl in ("full", "post"), wl in ("full", "climate")
     do_mesh = wl in ("full", "mesh")
+    do_plates = wl in ("full", "plates")
     # replicas: every rank processes its own copy of the same seeded planet (identical work per GPU, so the
     # N-GPU numbers are a clean weak-scaling series)
     inp = Inputs(args.cells, SEED, on_device=local)
@@ -337,17 +353,22 @@ def run_b200(args):
     if args.flood:
         dm.set_option("flood", args.flood)
 
-    r_plate = torch.from_numpy(inp.r_plate).to(dev)
-    r_super = torch.from_numpy(inp.r_super).to(dev)
+    r_plate = torch.empty(N, dtype=torch.int32, device=dev)
+    r_super = torch.empty(N, dtype=torch.int32, device=dev)
     delta = torch.empty(N, dtype=torch.float32, device=dev)
     ocean = torch.empty(N, dtype=torch.uint8, device=dev)
     koppen = torch.empty(N, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     state = {}
 
+    def plates_device():
+        pl.projectCoarsePlates(dm, None, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES, out=r_plate)
+        pl.smoothAndReconnectPlates(dm, r_plate, inp.seeds, 3)
+        state["super"] = pl.buildSuperPlates(dm, r_plate, inp.seeds, inp.vec, inp.pio, inp.dens, out=r_super)
+
     def elevation_device():
         res = assignElevation(dm, None, inp.pio, r_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
-                              inp.super_data(r_super))
+                              state["super"])
         state["elev"], state["hotspot"] = res["r_elevation"], res["debugLayers"]["hotspot"]
 
     def post_device():
@@ -355,10 +376,11 @@ def run_b200(args):
                           out_erosionDelta=delta, out_isOcean=ocean, timing=False)
 
     # untimed preparation of the inputs the chosen workload starts from
+    plates_device()
     elevation_device()
     pre = state["elev"].clone()
     land = int((pre > 0).sum().item())
-    if wl == "mesh":
+    if wl in ("mesh", "plates"):
         state["elev"] = pre
     if wl == "climate":
         post_device()
@@ -368,6 +390,8 @@ def run_b200(args):
         if do_mesh:
             dm.generateFibonacciSphere(args.cells, 0.75, SEED, out=xyz_t)
             dm.triangulateSphere(xyz_t, off_t, adj_t)
+        if do_plates:
+            plates_device()
         if do_elev:
             elevation_device()
         elif do_post:
@@ -438,7 +462,8 @@ def run_b200(args):
     h_off = torch.empty(N + 1, dtype=torch.int32).pin_memory()
     h_adj = torch.empty(E, dtype=torch.int32).pin_memory()
     np_xyz, np_off, np_adj = h_xyz.numpy(), h_off.numpy(), h_adj.numpy()
-    h_plate, h_super, h_pre, h_hot0 = pin(inp.r_plate), pin(inp.r_super), pin(pre.cpu().numpy()), pin(state["hotspot"].cpu().numpy())
+    r_plate_dev_final, r_super_dev_final = r_plate.clone(), r_super.clone()
+    h_plate, h_super, h_pre, h_hot0 = pin(r_plate.cpu().numpy()), pin(r_super.cpu().numpy()), pin(pre.cpu().numpy()), pin(state["hotspot"].cpu().numpy())
     h_elev = torch.empty(N, dtype=torch.float32).pin_memory()
     h_delta = torch.empty(N, dtype=torch.float32).pin_memory()
     h_ocean = torch.empty(N, dtype=torch.uint8).pin_memory()
@@ -446,10 +471,12 @@ def run_b200(args):
     np_delta, np_ocean, np_koppen, np_plate, np_super = h_delta.numpy(), h_ocean.numpy(), h_koppen.numpy(), h_plate.numpy(), h_super.numpy()
     if wl == "climate":
         h_elev.copy_(elev_dev_final.cpu())
-    h2d = (12 * N if do_mesh else 0) + (8 * N if do_elev else 0)     # mesh: r_xyz goes host → device for the triangulation + ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
-    d2h = (12 * N + 4 * (N + 1) + 4 * E if do_mesh else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
+    # mesh: r_xyz goes host → device for the triangulation; plates: r_plate in/out between the three calls
+    h2d = (12 * N if do_mesh else 0) + (4 * N + 4 * N if do_plates else 0) + (8 * N if do_elev else 0) + \
+          ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
+    d2h = (12 * N + 4 * (N + 1) + 4 * E if do_mesh else 0) + (4 * N + 4 * N + 4 * N if do_plates else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
           ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
-    reply, host = {}, {}
+    reply, host = {}, {"super": dict(state["super"], r_superPlate=np_super)}
 
     host_stage = {}
 
@@ -461,9 +488,14 @@ def run_b200(args):
             dm.generateFibonacciSphere(args.cells, 0.75, SEED, out=np_xyz)
             dm.triangulateSphere(np_xyz, np_off, np_adj)
         tt.append(time.perf_counter())
+        if do_plates:
+            pl.projectCoarsePlates(dm, None, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES, out=np_plate)
+            pl.smoothAndReconnectPlates(dm, np_plate, inp.seeds, 3)
+            host["super"] = pl.buildSuperPlates(dm, np_plate, inp.seeds, inp.vec, inp.pio, inp.dens, out=np_super)
+        tt.append(time.perf_counter())
         if do_elev:
             res = assignElevation(dm, None, inp.pio, np_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
-                                  inp.super_data(np_super))
+                                  host["super"])
             np_elev, np_hot = res["r_elevation"], res["debugLayers"]["hotspot"]
         elif do_post:
             h_elev.copy_(h_pre)
@@ -480,8 +512,8 @@ def run_b200(args):
                     reply[k] = res[k]     # device → host copy of every array of the climateDone message
         tt.append(time.perf_counter())
         host["elev"] = np_elev
-        host_stage.update(mesh_ms=1e3 * (tt[1] - tt[0]), elevation_ms=1e3 * (tt[2] - tt[1]), post_ms=1e3 * (tt[3] - tt[2]),
-                          climate_ms=1e3 * (tt[4] - tt[3]))
+        host_stage.update(mesh_ms=1e3 * (tt[1] - tt[0]), plates_ms=1e3 * (tt[2] - tt[1]), elevation_ms=1e3 * (tt[3] - tt[2]),
+                          post_ms=1e3 * (tt[4] - tt[3]), climate_ms=1e3 * (tt[5] - tt[4]))
 
     step_host()
     barrier()
@@ -496,7 +528,9 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = N * world * args.steps / e2e_s
     # host-pointer and device-pointer passes agree bit for bit
-    same = (wl == "mesh" or bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item())) and \
+    if do_plates:
+        mesh_same = mesh_same and bool((h_plate == r_plate_dev_final.cpu()).all().item()) and bool((h_super == r_super_dev_final.cpu()).all().item())
+    same = (wl in ("mesh", "plates") or bool((torch.from_numpy(np.ascontiguousarray(host["elev"])) == elev_dev_final.cpu()).all().item())) and \
         (not do_clim or bool((h_koppen == koppen.cpu()).all().item())) and mesh_same and \
         (not do_mesh or (bool((h_xyz == torch.from_numpy(xyz)).all().item()) and
                          bool((h_off == torch.from_numpy(mesh.adjOffset)).all().item()) and bool((h_adj == torch.from_numpy(mesh.adjList)).all().item())))
@@ -548,8 +582,9 @@ def run_b200(args):
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
                        "flood": args.flood or "device",
-                       "inputs": "plate tables (seeded synthetic stand-ins for the plate pipeline) are resident before the "
-                                 "timed region; points and mesh adjacency are rebuilt from (N, jitter, seed) inside every step"},
+                       "inputs": "the coarse stage's outputs (20 000-region coarse mesh + a seeded synthetic plate assignment on "
+                                 "it, standing in for generatePlates / assignOceanLand) are resident before the timed region; "
+                                 "points, mesh adjacency, r_plate and super plates are rebuilt inside every step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
@@ -652,7 +687,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "mesh", "sharded-sweeps"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "mesh", "plates", "sharded-sweeps"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],

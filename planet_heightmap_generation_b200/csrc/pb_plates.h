@@ -94,6 +94,32 @@ struct MajorityVoteK {
     }
 };
 
+// The same sweep as a fixed-point iteration.  The sequential result is the unique solution of the triangular system
+//     new[r] = vote(new[nb] for nb < r, old[nb] for nb > r, old[r]),
+// so any iteration that recomputes every cell from the current values until a whole sweep changes nothing ends at
+// exactly that solution (cell 0 is right after one sweep and stays right; a cell is right one sweep after its lower
+// neighbours are).  Changes are sparse and local (plate boundaries), so a handful of plain parallel sweeps replace
+// the latency-bound dependency chain of MajorityVoteK, which is kept as the fallback when the iteration does not settle.
+struct MajorityFixpointK {
+    Csr g; const int* old; int* cur; const uint8_t* isSeed; double threshold; int* changed;
+    PB_DEV void operator()(int r) const {
+        const int s = g.off[r], e = g.off[r + 1], deg = e - s;
+        int plates[32], counts[32], nDistinct = 0;
+        for (int j = s; j < e; j++) {
+            const int nb = g.adj[j];
+            const int p = nb < r ? ld_volatile(cur + nb) : old[nb];
+            bool found = false;
+            for (int k = 0; k < nDistinct; k++) if (plates[k] == p) { counts[k]++; found = true; break; }
+            if (!found) { plates[nDistinct] = p; counts[nDistinct] = 1; nDistinct++; }
+        }
+        const int mine = old[r];
+        int bestPlate = mine, bestCount = 0;
+        for (int k = 0; k < nDistinct; k++) if (counts[k] > bestCount) { bestCount = counts[k]; bestPlate = plates[k]; }
+        const int out = ((double)bestCount > (double)deg * threshold && !isSeed[r]) ? bestPlate : mine;
+        if (ld_volatile(cur + r) != out) { cur[r] = out; *changed = 1; }
+    }
+};
+
 // ---- components of equal plate ------------------------------------------------------------------------------------------
 struct PlateCcInitK {
     int* parent; int* size;
@@ -193,7 +219,7 @@ struct SuperPlatesOut {
 
 struct Plates {
     Mesh* m;
-    DevBuf<int> cOff, cAdj, cPlate, parent, size, scratch, pidx, area, first, toSuper, seedsDev;
+    DevBuf<int> cOff, cAdj, cPlate, parent, size, scratch, pidx, area, first, toSuper, seedsDev, oldPlate;
     DevBuf<float> cXyz;
     DevBuf<uint8_t> simplexTab, isSeed, inMain;
     DevBuf<unsigned long long> word, best;
@@ -242,15 +268,28 @@ struct Plates {
                 if (seeds[k] >= 0 && seeds[k] < N && at[k] == seeds[k]) dev_copy(isSeed.p + seeds[k], &one, 1, 0, s);
             stream_sync(s);
         }
-        if (numPasses > 0) {
-            word.ensure(N);
-            x.for_each(N, PlateWordPackK{r_plate, word.p, 0u});
-            for (int pass = 0; pass < numPasses; pass++)
-                x.ordered(N, MajorityVoteK{m->csr(), word.p, isSeed.p, (unsigned)(pass + 1), pass == 0 ? 0.4 : 0.5});
-            x.for_each(N, PlateWordUnpackK{word.p, r_plate});
+        scratch.ensure(4);
+        static const bool forceOrdered = getenv("PB_PLATES_ORDERED") != nullptr;     // measurement knob
+        for (int pass = 0; pass < numPasses; pass++) {
+            const double threshold = pass == 0 ? 0.4 : 0.5;
+            dev_copy(oldPlate.ensure(N), r_plate, sizeof(int) * (size_t)N, 2, s);
+            bool settled = false;
+            for (int it = 0; it < 64 && !forceOrdered; it++) {
+                dev_memset(scratch.p + 3, 0, sizeof(int), s);
+                x.for_each(N, MajorityFixpointK{m->csr(), oldPlate.p, r_plate, isSeed.p, threshold, scratch.p + 3});
+                int changed = 0;
+                dev_copy(&changed, scratch.p + 3, sizeof(int), 1, s);
+                stream_sync(s);
+                if (!changed) { settled = true; break; }
+            }
+            if (!settled) {      // long propagation chain: exact dependency-ordered sweep from the pass's start state
+                word.ensure(N);
+                x.for_each(N, PlateWordPackK{oldPlate.p, word.p, 0u});
+                x.ordered(N, MajorityVoteK{m->csr(), word.p, isSeed.p, 1u, threshold});
+                x.for_each(N, PlateWordUnpackK{word.p, r_plate});
+            }
         }
         // largest component per plate
-        scratch.ensure(4);
         dev_memset(scratch.p, 0, 4 * sizeof(int), s);
         x.for_each(N, IntMaxK{r_plate, scratch.p});
         int maxId = 0;

@@ -157,3 +157,35 @@ def synthetic_plate_tables(r_xyz: np.ndarray, elevation: np.ndarray, seed: int, 
         lut[pid] = group[pid]
     r_super = lut[r_plate].astype(np.int32)
     return r_plate, plates, ids, r_super, super_plates
+
+
+def synthetic_coarse_plates(coarse_xyz: np.ndarray, seed: int, n_plates: int = 40, ocean_fraction: float = 0.7):
+    """Seeded stand-in for generatePlates + assignOceanLand on the coarse mesh (js/coarse-plates.js:19-39): what
+    projectCoarsePlates / smoothAndReconnectPlates / buildSuperPlates / assignElevation receive from the coarse stage.
+    Returns (coarse_r_plate, plateSeeds list in Set order, plateVec, plateIsOcean, plateDensity).  Plates are weighted
+    spherical Voronoi regions of random seed regions (plate id = seed region id); plates turn oceanic in random order
+    until `ocean_fraction` of the area is ocean; poles are random unit vectors, omega in ±[0.5, 2.0) (js/plates.js:226-227),
+    densities are the worker's own draws makeRng(r + 777) (js/planet-worker.js:196-201)."""
+    p = np.asarray(coarse_xyz, np.float32).reshape(-1, 3).astype(np.float64)
+    nc = p.shape[0]
+    rng = np.random.default_rng(seed + 7919)
+    seeds = [int(s) for s in rng.choice(nc, size=n_plates, replace=False)]
+    weight = 1.0 + 0.35 * rng.random(n_plates)
+    owner = np.argmax((p @ p[seeds].T) * weight, axis=1)
+    owner[seeds] = np.arange(n_plates)
+    coarse_r_plate = np.asarray(seeds, np.int32)[owner]
+    area = np.bincount(owner, minlength=n_plates)
+    plate_is_ocean, acc = set(), 0
+    for k in rng.permutation(n_plates):
+        if acc >= ocean_fraction * nc:
+            break
+        plate_is_ocean.add(seeds[k])
+        acc += int(area[k])
+    plate_vec, plate_density = {}, {}
+    for s in seeds:
+        pole = rng.normal(size=3)
+        pole /= np.linalg.norm(pole)
+        plate_vec[s] = {"pole": [float(v) for v in pole], "omega": float((0.5 + rng.random() * 1.5) * (-1 if rng.random() < 0.5 else 1))}
+        d = park_miller(s + 777, 2)
+        plate_density[s] = float(3.0 + d[0] * 0.5) if s in plate_is_ocean else float(2.4 + d[1] * 0.5)
+    return coarse_r_plate, seeds, plate_vec, plate_is_ocean, plate_density
