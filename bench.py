@@ -93,23 +93,16 @@ def get_planet(cells: int, seed: int = SEED, on_device: int | None = None):
 NMAG, SPREAD = 0.40, 5       # Roughness slider default (index.html) and the worker's fixed spread (planet-worker.js:138)
 
 
-NUM_PLATES, N_COARSE = 40, 20000
+# index.html slider defaults: 80 plates, 4 continents, size variety 0, land coverage 0.30
+NUM_PLATES, NUM_CONTINENTS, SIZE_VARIETY, LAND_COVERAGE, N_COARSE = 80, 4, 0.0, 0.30, 20000
 
 
 class Inputs:
-    """What the path receives from the coarse stage (generateCoarsePlates, js/coarse-plates.js:19-39): the 20 000-region
-    coarse mesh of buildSphere(N_COARSE, 0.75, makeRng(seed + 137)) — built by the same device / checker code as the main
-    mesh — and a seeded synthetic plate assignment on it (sphere.synthetic_coarse_plates).  Everything downstream
-    (r_plate, super plates) is computed by the path itself."""
+    """The seeded planet both arms work on: (N, jitter 0.75, seed) → mesh + r_xyz.  Everything downstream — coarse
+    plates, r_plate, super plates, elevation … — is computed by the arm itself from the seed and the slider defaults."""
 
     def __init__(self, cells: int, seed: int = SEED, on_device: int | None = None):
-        from planet_heightmap_generation_b200.sphere import synthetic_coarse_plates
         self.mesh, self.xyz = get_planet(cells, SEED, on_device)
-        self.cmesh, self.cxyz = get_planet(N_COARSE, SEED + 137, on_device)
-        self.crp, self.seeds, self.vec, self.pio, self.dens = synthetic_coarse_plates(self.cxyz, seed, NUM_PLATES)
-        # oracle-side plate table, plateSeeds order
-        self.plates = {s: dict(isOcean=s in self.pio, pole=tuple(self.vec[s]["pole"]), omega=self.vec[s]["omega"],
-                               density=self.dens[s]) for s in self.seeds}
 
 
 def workload_name(cells, hiters, workload):
@@ -117,7 +110,8 @@ def workload_name(cells, hiters, workload):
     post = (f"runPostProcessing with default sliders, hIters={hiters} K=0.0003 m=0.5 tIters=1 gIters=5, smooth 1, "
             f"ridge 3, creep 3")
     clim = "computeWind+computeOceanCurrents+computePrecipitation+computeTemperature+classifyKoppen (default offsets)"
-    plat = f"projectCoarsePlates ({NUM_PLATES} plates on the {N_COARSE}-region coarse mesh) + smoothAndReconnectPlates(3) + buildSuperPlates"
+    plat = (f"generateCoarsePlates ({NUM_PLATES} plates, {NUM_CONTINENTS} continents, land {LAND_COVERAGE}, {N_COARSE}-region coarse mesh) + "
+            f"projectCoarsePlates + smoothAndReconnectPlates(3) + buildSuperPlates")
     tri = "buildSphere (Fibonacci points with seeded jitter + pole, spherical Delaunay adjacency in the SphereMesh constructor's order)"
     what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri, "plates": plat,
             "full": " then ".join([tri, plat, elev, post, clim])}[workload]
@@ -200,13 +194,21 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
     pstate = {}
 
     def plates():
-        rp = oracle.project_coarse_plates(mesh, xyz, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES)
-        oracle.smooth_and_reconnect_plates(mesh, rp, inp.seeds, 3)
-        rs, sp = oracle.build_super_plates(mesh, rp, inp.plates)
-        pstate.update(r_plate=rp, r_super=rs, super=sp)
+        from planet_heightmap_generation_b200.sphere import park_miller
+        cp = oracle.generate_coarse_plates(SEED, NUM_PLATES, NUM_CONTINENTS, SIZE_VARIETY, LAND_COVERAGE, N_COARSE)
+        seeds, pio = cp["coarsePlateSeeds"], cp["coarsePlateIsOcean"]
+        rp = oracle.project_coarse_plates(mesh, xyz, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], SEED, NUM_PLATES)
+        oracle.smooth_and_reconnect_plates(mesh, rp, seeds, 3)
+        table = {}
+        for s in seeds:                                       # plate densities: js/planet-worker.js:196-201
+            d = park_miller(s + 777, 2)
+            table[s] = dict(isOcean=s in pio, pole=tuple(cp["coarsePlateVec"][s]["pole"]), omega=cp["coarsePlateVec"][s]["omega"],
+                            density=float(3.0 + d[0] * 0.5) if s in pio else float(2.4 + d[1] * 0.5))
+        rs, sp = oracle.build_super_plates(mesh, rp, table)
+        pstate.update(r_plate=rp, r_super=rs, super=sp, seeds=seeds, pio=pio, table=table)
 
     def elevation():
-        oe.assign(pstate["r_plate"], inp.plates, inp.seeds, SEED, NMAG, SEED, SPREAD, pstate["r_super"], pstate["super"])
+        oe.assign(pstate["r_plate"], pstate["table"], pstate["seeds"], SEED, NMAG, SEED, SPREAD, pstate["r_super"], pstate["super"])
         return oe.get("r_elevation"), oe.get("hotspot")
 
     plates()
@@ -240,7 +242,7 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload):
             oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, h, hiters)
         t2 = time.perf_counter()
         if workload in ("full", "climate"):
-            clim.run_all(eroded if workload == "climate" else e, inp.pio, pstate["r_plate"], SEED)
+            clim.run_all(eroded if workload == "climate" else e, pstate["pio"], pstate["r_plate"], SEED)
         t3 = time.perf_counter()
         if i >= warmup:
             times.append(t3 - t)
@@ -361,13 +363,21 @@ def run_b200(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     state = {}
 
+    def plate_stage(rp, rs):
+        """generateCoarsePlates → projectCoarsePlates → smoothAndReconnectPlates → buildSuperPlates (planet-worker.js:160-211)"""
+        cp = pl.generateCoarsePlates(dm, SEED, NUM_PLATES, NUM_CONTINENTS, SIZE_VARIETY, LAND_COVERAGE, N_COARSE)
+        seeds, vec, pio, dens = cp["coarsePlateSeeds"], cp["coarsePlateVec"], cp["coarsePlateIsOcean"], cp["plateDensity"]
+        pl.projectCoarsePlates(dm, None, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], SEED, NUM_PLATES, out=rp)
+        cp["coarseMesh"].close()
+        pl.smoothAndReconnectPlates(dm, rp, seeds, 3)
+        sp = pl.buildSuperPlates(dm, rp, seeds, vec, pio, dens, out=rs)
+        return dict(seeds=seeds, vec=vec, pio=pio, dens=dens, super=sp)
+
     def plates_device():
-        pl.projectCoarsePlates(dm, None, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES, out=r_plate)
-        pl.smoothAndReconnectPlates(dm, r_plate, inp.seeds, 3)
-        state["super"] = pl.buildSuperPlates(dm, r_plate, inp.seeds, inp.vec, inp.pio, inp.dens, out=r_super)
+        state.update(plate_stage(r_plate, r_super))
 
     def elevation_device():
-        res = assignElevation(dm, None, inp.pio, r_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
+        res = assignElevation(dm, None, state["pio"], r_plate, state["vec"], state["seeds"], SEED, NMAG, SEED, SPREAD, state["dens"],
                               state["super"])
         state["elev"], state["hotspot"] = res["r_elevation"], res["debugLayers"]["hotspot"]
 
@@ -399,7 +409,7 @@ def run_b200(args):
         if do_post:
             post_device()
         if do_clim:
-            cl.computeClimate(dm, state["elev"], inp.pio, r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
+            cl.computeClimate(dm, state["elev"], state["pio"], r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
 
     def barrier():
         torch.cuda.synchronize()
@@ -476,7 +486,7 @@ def run_b200(args):
           ((8 * N if not do_elev else 0) if do_post else 0) + (8 * N if do_clim else 0)
     d2h = (12 * N + 4 * (N + 1) + 4 * E if do_mesh else 0) + (4 * N + 4 * N + 4 * N if do_plates else 0) + ((4 + 4 + 3 + 4 * len(DEBUG_LAYERS)) * N if do_elev else 0) + (9 * N if do_post else 0) + \
           ((4 * len(CLIMATE_REPLY_F32) + 1) * N + 3 * 4 * 360 if do_clim else 0)
-    reply, host = {}, {"super": dict(state["super"], r_superPlate=np_super)}
+    reply, host = {}, dict(state, super=dict(state["super"], r_superPlate=np_super))
 
     host_stage = {}
 
@@ -489,12 +499,10 @@ def run_b200(args):
             dm.triangulateSphere(np_xyz, np_off, np_adj)
         tt.append(time.perf_counter())
         if do_plates:
-            pl.projectCoarsePlates(dm, None, inp.cmesh, inp.cxyz, inp.crp, SEED, NUM_PLATES, out=np_plate)
-            pl.smoothAndReconnectPlates(dm, np_plate, inp.seeds, 3)
-            host["super"] = pl.buildSuperPlates(dm, np_plate, inp.seeds, inp.vec, inp.pio, inp.dens, out=np_super)
+            host.update(plate_stage(np_plate, np_super))
         tt.append(time.perf_counter())
         if do_elev:
-            res = assignElevation(dm, None, inp.pio, np_plate, inp.vec, inp.seeds, SEED, NMAG, SEED, SPREAD, inp.dens,
+            res = assignElevation(dm, None, host["pio"], np_plate, host["vec"], host["seeds"], SEED, NMAG, SEED, SPREAD, host["dens"],
                                   host["super"])
             np_elev, np_hot = res["r_elevation"], res["debugLayers"]["hotspot"]
         elif do_post:
@@ -505,7 +513,7 @@ def run_b200(args):
                               out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
         tt.append(time.perf_counter())
         if do_clim:
-            w, o, p, t, _ = cl.computeClimate(dm, np_elev, inp.pio, np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
+            w, o, p, t, _ = cl.computeClimate(dm, np_elev, host["pio"], np_plate, SEED, 0.0, 0.0, 0.3, out_koppen=np_koppen)
             for res, keys in ((w, CLIMATE_REPLY_F32[:4] + ["itczLons", "itczLatsSummer", "itczLatsWinter"]),
                               (o, CLIMATE_REPLY_F32[4:12]), (p, CLIMATE_REPLY_F32[12:14]), (t, CLIMATE_REPLY_F32[14:])):
                 for k in keys:
@@ -582,9 +590,8 @@ def run_b200(args):
                        "l2": "256 MiB buffer written between steps (inside the timed region)",
                        "land_cells": land,
                        "flood": args.flood or "device",
-                       "inputs": "the coarse stage's outputs (20 000-region coarse mesh + a seeded synthetic plate assignment on "
-                                 "it, standing in for generatePlates / assignOceanLand) are resident before the timed region; "
-                                 "points, mesh adjacency, r_plate and super plates are rebuilt inside every step"},
+                       "inputs": "only (N, jitter, seed) and the slider defaults: points, mesh adjacency, coarse plates, r_plate and "
+                                 "super plates are rebuilt inside every step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},

@@ -235,6 +235,20 @@ pb_status pb_smooth_and_reconnect_plates(pb_mesh* mesh, int32_t* r_plate, const 
 pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_plate_table* plates, int32_t* r_superPlate,
                                 pb_super_plate_table* superOut);
 
+/* pb_generate_coarse_plates replaces generateCoarsePlates(seed, numPlates, numContinents, continentSizeVariety,
+ * landCoverage) (js/coarse-plates.js:19-39 = buildSphere(N_COARSE, 0.75, makeRng(seed + 137)) + generatePlates,
+ * js/plates.js:6-232 + assignOceanLand, js/ocean-land.js:7-238).  numCoarse is the reference's N_COARSE (20000).
+ * Host arrays only: coarse_xyz[3*(numCoarse+1)], coarse_r_plate[numCoarse+1]; the plate table (caller-allocated,
+ * capacity >= numPlates) lists the plates in plateSeeds order with pole/omega (coarsePlateVec), isOcean
+ * (coarsePlateIsOcean) and the density the worker draws for each plate (js/planet-worker.js:196-201).  The coarse mesh
+ * comes back as an ordinary pb_mesh (pb_mesh_get_adjacency gives its CSR arrays; destroy it with pb_mesh_destroy). */
+typedef struct pb_plate_table_out {
+    int32_t capacity; int32_t n; int32_t* ids; uint8_t* isOcean; double* pole /* 3 per plate */; double* omega; double* density;
+} pb_plate_table_out;
+pb_status pb_generate_coarse_plates(pb_context* ctx, double seed, int32_t numPlates, int32_t numContinents,
+                                    double continentSizeVariety, double landCoverage, int32_t numCoarse, pb_mesh** coarseMesh,
+                                    float* coarse_xyz, int32_t* coarse_r_plate, pb_plate_table_out* plates);
+
 /* ---- mesh construction ------------------------------------------------------------------
  * pb_triangulate_sphere replaces the triangulation inside buildSphere and the SphereMesh constructor's adjacency
  * (js/sphere-mesh.js:94-146, 174-186; Delaunator 5.0.1 + addPoleToMesh): r_xyz holds numRegions unit vectors (the

@@ -354,3 +354,24 @@ def build_super_plates(mesh, r_plate, plates):
     table = {sp: dict(isOcean=bool(sp_oc[sp]), pole=tuple(sp_pole[3 * sp:3 * sp + 3]), omega=float(sp_om[sp]), density=float(sp_de[sp]))
              for sp in range(n)}
     return r_super, table
+
+
+def generate_coarse_plates(seed, num_plates, num_continents, continent_size_variety=0.0, land_coverage=0.3, n_coarse=20000):
+    """generateCoarsePlates (js/coarse-plates.js:19-39): coarse mesh of buildSphere(n_coarse, 0.75, makeRng(seed + 137)),
+    generatePlates (js/plates.js:6-232) and assignOceanLand (js/ocean-land.js:7-238) on it.
+    Returns dict(coarseMesh, coarse_xyz, coarse_r_plate, coarsePlateSeeds, coarsePlateVec, coarsePlateIsOcean)."""
+    from .mesh_hull import build_sphere_from_points
+    cmesh, cxyz = build_sphere_from_points(fibonacci_sphere(n_coarse, 0.75, seed + 137))
+    n = cmesh.numRegions
+    r_plate = np.empty(n, np.int32)
+    seeds = np.zeros(num_plates, np.int32)
+    pole, omega, oc = np.zeros(3 * num_plates), np.zeros(num_plates), np.zeros(num_plates, np.uint8)
+    lib().orc_generate_coarse_plates.restype = C.c_int
+    k = lib().orc_generate_coarse_plates(*_mesh_args(cmesh), _p(cxyz, C.c_float), C.c_double(seed), C.c_int(num_plates),
+                                         C.c_int(num_continents), C.c_double(continent_size_variety), C.c_double(land_coverage),
+                                         _p(r_plate, C.c_int32), _p(seeds, C.c_int32), _p(pole, C.c_double), _p(omega, C.c_double),
+                                         _p(oc, C.c_uint8))
+    ids = [int(s) for s in seeds[:k]]
+    return dict(coarseMesh=cmesh, coarse_xyz=cxyz, coarse_r_plate=r_plate, coarsePlateSeeds=ids,
+                coarsePlateVec={s: {"pole": [float(v) for v in pole[3 * i:3 * i + 3]], "omega": float(omega[i])} for i, s in enumerate(ids)},
+                coarsePlateIsOcean={s for i, s in enumerate(ids) if oc[i]})

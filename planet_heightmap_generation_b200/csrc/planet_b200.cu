@@ -7,6 +7,7 @@
 #include "pb_shard.h"
 #include "pb_meshgen.h"
 #include "pb_plates.h"
+#include "pb_coarse.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -408,6 +409,9 @@ pb_status pb_climate_get(pb_climate* climate, const char* name, void* out) {
     });
 }
 
+static void triangulate(pb_context* ctx, int n, const float* xyz, bool hostPtrs, std::vector<int>* hOff, std::vector<int>* hAdj,
+                        int32_t* outOff, int32_t* outAdj);
+
 // ---- plate pipeline on the hi-res mesh -------------------------------------------------------------------------------
 static pb::Plates& plates_of(pb_mesh* mesh) {
     if (!mesh->plates) mesh->plates.reset(new pb::Plates(&mesh->m));
@@ -455,6 +459,49 @@ pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_
         }
         m.arg_back(r_superPlate, dSuper, (size_t)m.N);
         m.finish();
+    });
+}
+
+// generateCoarsePlates: coarse mesh on the device, growth / ocean-land logic on the host, smoothing on the device
+pb_status pb_generate_coarse_plates(pb_context* ctx, double seed, int32_t numPlates, int32_t numContinents, double continentSizeVariety,
+                                    double landCoverage, int32_t numCoarse, pb_mesh** coarseMesh, float* coarse_xyz,
+                                    int32_t* coarse_r_plate, pb_plate_table_out* plates) {
+    return guard([&] {
+        need(ctx && coarseMesh && coarse_xyz && coarse_r_plate && plates, "NULL argument");
+        need(numPlates >= 1 && numCoarse >= 4, "numPlates >= 1 and numCoarse >= 4 required");
+        need(plates->capacity >= numPlates && plates->ids && plates->isOcean && plates->pole && plates->omega && plates->density,
+             "plate table capacity below numPlates");
+        ctx->c.bind();
+        const pb::Exec& ex = ctx->c.ex;
+        const int n = numCoarse + 1;
+        if (!ctx->fib) ctx->fib.reset(new pb::FibonacciSphere());
+        pb::DevBuf<float> dXyz;
+        ctx->fib->generate(ex, numCoarse, 0.75, seed + 137, dXyz.ensure(3 * (size_t)n));     // COARSE_JITTER, isolated RNG (:12, 20)
+        pb::dev_copy(coarse_xyz, dXyz.p, sizeof(float) * 3 * (size_t)n, 1, ex.stream);
+        pb::stream_sync(ex.stream);
+        std::vector<int> hOff, hAdj;
+        const int savedMode = ctx->c.pointerMode;
+        triangulate(ctx, n, coarse_xyz, true, &hOff, &hAdj, nullptr, nullptr);
+        std::unique_ptr<pb_mesh> cm(new pb_mesh(&ctx->c, n, hOff.data(), hAdj.data(), coarse_xyz));
+        pb::CoarsePlatesResult R;
+        pb::Plates& P = plates_of(cm.get());
+        pb::DevBuf<int> dPlate;
+        auto smooth = [&](std::vector<int>& plate, const std::vector<int>& seeds, int passes) {
+            pb::dev_copy(dPlate.ensure(n), plate.data(), sizeof(int) * (size_t)n, 0, ex.stream);
+            P.smooth_and_reconnect(dPlate.p, seeds.data(), (int)seeds.size(), passes);
+            pb::dev_copy(plate.data(), dPlate.p, sizeof(int) * (size_t)n, 1, ex.stream);
+            pb::stream_sync(ex.stream);
+        };
+        pb::CoarseStage::generate_plates(n, hOff.data(), hAdj.data(), coarse_xyz, numPlates, seed, smooth, R);
+        pb::CoarseStage::ocean_land(n, hOff.data(), hAdj.data(), coarse_xyz, seed, numContinents, continentSizeVariety, landCoverage, R);
+        (void)savedMode;
+        memcpy(coarse_r_plate, R.r_plate.data(), sizeof(int) * (size_t)n);
+        plates->n = (int32_t)R.seeds.size();
+        for (size_t k = 0; k < R.seeds.size(); k++) {
+            plates->ids[k] = R.seeds[k]; plates->isOcean[k] = R.isOcean[k]; plates->omega[k] = R.omega[k]; plates->density[k] = R.density[k];
+            for (int c = 0; c < 3; c++) plates->pole[3 * k + c] = R.pole[3 * k + c];
+        }
+        *coarseMesh = cm.release();
     });
 }
 

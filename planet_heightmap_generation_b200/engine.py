@@ -70,6 +70,23 @@ class DeviceMesh:
         self.lib.check(self.lib.dll.pb_generate_fibonacci_sphere(self._ctx, int(N), float(jitter), float(seed), xyz.ctypes.data))
         return self._finish_from_points(xyz)
 
+    @classmethod
+    def _adopt(cls, parent: "DeviceMesh", mesh_handle, r_xyz) -> "DeviceMesh":
+        """Wrap a pb_mesh created by the library on `parent`'s context (the coarse mesh of generateCoarsePlates)."""
+        self = cls.__new__(cls)
+        self.lib, self.device = parent.lib, parent.device
+        self._ctx, self._owns_ctx, self._parent = parent._ctx, False, parent
+        self._mesh = mesh_handle
+        self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
+        self.numRegions = self.r_xyz.shape[0] // 3
+        d = self.lib.dll
+        self.numEdges = int(d.pb_mesh_num_edges(self._mesh))
+        self.adjOffset = np.empty(self.numRegions + 1, np.int32)
+        self.adjList = np.empty(self.numEdges, np.int32)
+        self.lib.check(d.pb_mesh_get_adjacency(self._mesh, self.adjOffset.ctypes.data, self.adjList.ctypes.data))
+        self._mode = parent._mode
+        return self
+
     def _finish_from_points(self, r_xyz):
         self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
         self.numRegions = self.r_xyz.shape[0] // 3
@@ -87,9 +104,9 @@ class DeviceMesh:
         if getattr(self, "_mesh", None):
             self.lib.dll.pb_mesh_destroy(self._mesh)
             self._mesh = None
-        if getattr(self, "_ctx", None):
+        if getattr(self, "_ctx", None) and getattr(self, "_owns_ctx", True):
             self.lib.dll.pb_context_destroy(self._ctx)
-            self._ctx = None
+        self._ctx = None
 
     def __del__(self):
         try:

@@ -1,6 +1,7 @@
 """Host mirror of the plate pipeline on the hi-res mesh: same names, argument order and
 result keys as the reference's functions, over the C ABI (csrc/pb_plates.h).
 
+  generateCoarsePlates       js/coarse-plates.js:19-39  (+ generatePlates js/plates.js:6-232, assignOceanLand js/ocean-land.js:7-238)
   projectCoarsePlates        js/coarse-plates.js:51-117
   smoothAndReconnectPlates   js/plates.js:241-348
   buildSuperPlates           js/super-plates.js:16-273
@@ -83,3 +84,36 @@ def buildSuperPlates(mesh: DeviceMesh, r_plate, plateSeeds, plateVec, plateIsOce
             "superPlateIsOcean": {i for i in range(k) if sp_oc[i]},
             "superPlateDensity": {i: float(sp_dens[i]) for i in range(k)},
             "numSuperPlates": k}
+
+
+class PlateTableOut(C.Structure):
+    _fields_ = [("capacity", C.c_int32), ("n", C.c_int32), ("ids", C.c_void_p), ("isOcean", C.c_void_p), ("pole", C.c_void_p),
+                ("omega", C.c_void_p), ("density", C.c_void_p)]
+
+
+N_COARSE = 20000     # js/coarse-plates.js:11
+
+
+def generateCoarsePlates(mesh: DeviceMesh, seed, numPlates, numContinents, continentSizeVariety=0.0, landCoverage=0.3,
+                         numCoarse: int = N_COARSE):
+    """→ {coarseMesh, coarse_xyz, coarse_r_plate, coarsePlateSeeds, coarsePlateVec, coarsePlateIsOcean} (+ plateDensity, the
+    worker's per-plate draws, js/planet-worker.js:196-201).  `mesh` only supplies the GPU context (the reference's function
+    takes none); coarseMesh is a DeviceMesh on the same context."""
+    p = int(numPlates)
+    n = int(numCoarse) + 1
+    ids, oc = np.zeros(p, np.int32), np.zeros(p, np.uint8)
+    pole, omega, dens = np.zeros(3 * p), np.zeros(p), np.zeros(p)
+    table = PlateTableOut(p, 0, ids.ctypes.data, oc.ctypes.data, pole.ctypes.data, omega.ctypes.data, dens.ctypes.data)
+    cxyz = np.empty(3 * n, np.float32)
+    crp = np.empty(n, np.int32)
+    handle = C.c_void_p()
+    mesh.lib.check(mesh.lib.dll.pb_generate_coarse_plates(mesh._ctx, float(seed), p, int(numContinents), float(continentSizeVariety),
+                                                          float(landCoverage), int(numCoarse), C.byref(handle), cxyz.ctypes.data,
+                                                          crp.ctypes.data, C.addressof(table)))
+    k = int(table.n)
+    seeds = [int(s) for s in ids[:k]]
+    return {"coarseMesh": DeviceMesh._adopt(mesh, handle, cxyz), "coarse_xyz": cxyz, "coarse_r_plate": crp,
+            "coarsePlateSeeds": seeds,
+            "coarsePlateVec": {s: {"pole": [float(v) for v in pole[3 * i:3 * i + 3]], "omega": float(omega[i])} for i, s in enumerate(seeds)},
+            "coarsePlateIsOcean": {s for i, s in enumerate(seeds) if oc[i]},
+            "plateDensity": {s: float(dens[i]) for i, s in enumerate(seeds)}}

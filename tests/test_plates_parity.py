@@ -137,3 +137,34 @@ def test_plate_pipeline_device_pointers_1M(cuda_lib, oracle):
     assert np.array_equal(res["r_superPlate"].cpu().numpy(), o_super)
     assert res["numSuperPlates"] == len(o_table)
     dm.close()
+
+
+@pytest.mark.parametrize("seed,P,cont,variety,cover,nc", [(42, 80, 4, 0.0, 0.3, 20000), (7, 12, 3, 0.5, 0.3, 4000), (123456, 40, 6, 1.0, 0.45, 6000),
+                                                           (3, 5, 8, 0.0, 0.2, 3000), (99, 150, 2, 0.3, 0.3, 5000)])
+def test_generate_coarse_plates_matches_oracle(backend, oracle, seed, P, cont, variety, cover, nc):
+    """generateCoarsePlates = coarse buildSphere + generatePlates + assignOceanLand: plate ids, seed order, Euler poles,
+    ocean flags and the worker's densities, bit for bit."""
+    from planet_heightmap_generation_b200.sphere import park_miller
+    mesh, xyz, nd, elev = make_planet(oracle, 3000)
+    dm = DeviceMesh(mesh, xyz, lib=backend)
+    got = pl.generateCoarsePlates(dm, seed, P, cont, variety, cover, numCoarse=nc)
+    want = oracle.generate_coarse_plates(seed, P, cont, variety, cover, n_coarse=nc)
+    cm = got["coarseMesh"]
+    assert np.array_equal(cm.adjOffset, want["coarseMesh"].adjOffset) and np.array_equal(cm.adjList, want["coarseMesh"].adjList)
+    assert (got["coarse_xyz"].view(np.uint32) == want["coarse_xyz"].view(np.uint32)).all()
+    assert got["coarsePlateSeeds"] == want["coarsePlateSeeds"] and len(got["coarsePlateSeeds"]) == min(P, nc + 1)
+    assert np.array_equal(got["coarse_r_plate"], want["coarse_r_plate"])
+    assert got["coarsePlateIsOcean"] == want["coarsePlateIsOcean"]
+    for s in want["coarsePlateSeeds"]:
+        assert got["coarsePlateVec"][s]["pole"] == want["coarsePlateVec"][s]["pole"]
+        assert got["coarsePlateVec"][s]["omega"] == want["coarsePlateVec"][s]["omega"]
+        d = park_miller(s + 777, 2)
+        assert got["plateDensity"][s] == (3.0 + d[0] * 0.5 if s in want["coarsePlateIsOcean"] else 2.4 + d[1] * 0.5)
+    # every region belongs to a seeded plate and the land share is near the requested coverage
+    area = np.bincount(got["coarse_r_plate"], minlength=nc + 1)
+    assert area[got["coarsePlateSeeds"]].sum() == nc + 1
+    # the coarse mesh is an ordinary mesh of the same context: the projection runs straight from it
+    r_plate = pl.projectCoarsePlates(dm, xyz, cm, got["coarse_xyz"], got["coarse_r_plate"], seed, P)
+    assert np.array_equal(r_plate, oracle.project_coarse_plates(mesh, xyz, want["coarseMesh"], want["coarse_xyz"], want["coarse_r_plate"], seed, P))
+    cm.close()
+    dm.close()
