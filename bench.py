@@ -317,6 +317,92 @@ def algorithmic_bytes(name: str, N: int, E: int, land: int):
 
 
 # ---------------------------------------------------------------------------------------------------
+# several planets in flight on one GPU (one context + stream + host thread per planet)
+# ---------------------------------------------------------------------------------------------------
+def pipelined_throughput(args, mesh, xyz, local, planets: int, steps: int):
+    """The step is latency-bound (one dependent chain of heap pops on one SM, host-serial fills), so a GPU that
+    generates many planets keeps several in flight: every planet has its own pb_context, CUDA stream and host thread
+    and runs the same full pipeline as the single-planet step.  Returns seconds for `steps` steps of every planet
+    (host wall clock around a device-wide synchronize on both sides)."""
+    import threading
+
+    import torch
+    from planet_heightmap_generation_b200 import climate as cl
+    from planet_heightmap_generation_b200 import plates as pl
+    from planet_heightmap_generation_b200.elevation import assignElevation
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    from planet_heightmap_generation_b200.terrain_post import runPostProcessing
+    dev = torch.device("cuda", local)
+    N, E = mesh.numRegions, int(mesh.adjList.shape[0])
+
+    class Job:
+        def __init__(self):
+            self.dm = DeviceMesh(mesh, xyz, device=local)
+            if args.flood:
+                self.dm.set_option("flood", args.flood)
+            self.stream = torch.cuda.Stream(device=dev)
+            i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+            self.xyz = torch.empty(3 * N, dtype=f32, device=dev)
+            self.off, self.adj = torch.empty(N + 1, dtype=i32, device=dev), torch.empty(E, dtype=i32, device=dev)
+            self.r_plate, self.r_super = torch.empty(N, dtype=i32, device=dev), torch.empty(N, dtype=i32, device=dev)
+            self.delta = torch.empty(N, dtype=f32, device=dev)
+            self.ocean, self.koppen = torch.empty(N, dtype=u8, device=dev), torch.empty(N, dtype=u8, device=dev)
+            self.error = None
+
+        def step(self):
+            dm = self.dm
+            dm.generateFibonacciSphere(args.cells, 0.75, SEED, out=self.xyz)
+            dm.triangulateSphere(self.xyz, self.off, self.adj)
+            cp = pl.generateCoarsePlates(dm, SEED, NUM_PLATES, NUM_CONTINENTS, SIZE_VARIETY, LAND_COVERAGE, N_COARSE)
+            seeds, vec, pio, dens = cp["coarsePlateSeeds"], cp["coarsePlateVec"], cp["coarsePlateIsOcean"], cp["plateDensity"]
+            pl.projectCoarsePlates(dm, None, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], SEED, NUM_PLATES, out=self.r_plate)
+            cp["coarseMesh"].close()
+            pl.smoothAndReconnectPlates(dm, self.r_plate, seeds, 3)
+            sp = pl.buildSuperPlates(dm, self.r_plate, seeds, vec, pio, dens, out=self.r_super)
+            res = assignElevation(dm, None, pio, self.r_plate, vec, seeds, SEED, NMAG, SEED, SPREAD, dens, sp)
+            elev = res["r_elevation"]
+            runPostProcessing(dm, None, elev, SLIDERS, None, SEED, res["debugLayers"]["hotspot"], hItersOverride=args.hiters,
+                              out_erosionDelta=self.delta, out_isOcean=self.ocean, timing=False)
+            cl.computeClimate(dm, elev, pio, self.r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=self.koppen)
+            self.elev = elev
+
+        def run(self, k):
+            try:
+                torch.cuda.set_device(local)
+                with torch.cuda.stream(self.stream):
+                    for _ in range(k):
+                        self.step()
+                    self.stream.synchronize()
+            except Exception as e:      # surfaced by the caller
+                self.error = e
+
+    jobs = [Job() for _ in range(planets)]
+
+    def run_all(k):
+        threads = [threading.Thread(target=j.run, args=(k,)) for j in jobs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for j in jobs:
+            if j.error:
+                raise j.error
+
+    run_all(1)                                   # warm-up: allocations, caches
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_all(steps)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    first = jobs[0]
+    agree = all(bool((j.elev == first.elev).all().item()) and bool((j.koppen == first.koppen).all().item()) for j in jobs[1:])
+    ref = (first.elev.clone(), first.koppen.clone())
+    for j in jobs:
+        j.dm.close()
+    return secs, agree, ref
+
+
+# ---------------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -580,6 +666,20 @@ def run_b200(args):
                                      " (qhull convex hull + SphereMesh constructor, scipy)" if wl == "mesh" else ""),
                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages": stages}
 
+    # ---- several planets in flight (supplementary: `value` above is one planet at a time) ----------------------
+    in_flight = None
+    if wl == "full" and args.in_flight > 1:
+        secs, agree, ref = pipelined_throughput(args, mesh, xyz, local, args.in_flight, args.steps)
+        if world > 1:
+            t = torch.tensor([secs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        in_flight = {"planets_in_flight_per_gpu": args.in_flight, "value": N * world * args.in_flight * args.steps / secs, "unit": UNIT,
+                     "seconds": secs, "steps_per_planet": args.steps,
+                     "matches_single_planet_path": bool(agree and (ref[0] == elev_dev_final).all().item() and (ref[1] == koppen).all().item()),
+                     "note": "one pb_context + CUDA stream + host thread per planet, same full pipeline per planet; host wall clock "
+                             "around device synchronizes"}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -596,7 +696,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
-            "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "library": dm.lib.version,
+            "cpu_baseline": cpu_baseline, "throughput_in_flight": in_flight, "kernel_breakdown": breakdown, "library": dm.lib.version,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -699,6 +799,8 @@ def main():
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],
                     help="engine option: where the serial heap pass of priorityFloodCarve runs (default device)")
+    ap.add_argument("--in-flight", type=int, default=4, dest="in_flight",
+                    help="planets kept in flight per GPU for the supplementary throughput figure of the full workload (0/1: skip)")
     ap.add_argument("--cells", type=int, default=1_000_000)
     ap.add_argument("--hiters", type=int, default=50)
     ap.add_argument("--dominant", default="", help="kernel whose launches are event-timed for the roofline "

@@ -17,6 +17,7 @@
 #include <vector>
 #include <stdexcept>
 #include <algorithm>
+#include <atomic>
 #include <typeinfo>
 #include <map>
 #include <cxxabi.h>
@@ -165,7 +166,7 @@ PB_DEV int word_seq(unsigned long long w) { return (int)(w >> 32); }
 // launches
 // ---------------------------------------------------------------------------------------------
 struct LaunchStats {
-    long long launches = 0;  // kernels launched through this layer since the last reset
+    std::atomic<long long> launches{0};  // kernels launched through this layer (contexts may run on several host threads)
 };
 inline LaunchStats& launch_stats() {
     static LaunchStats s;
