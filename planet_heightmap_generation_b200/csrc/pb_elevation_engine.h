@@ -114,11 +114,20 @@ struct Elevation {
             frontier.swap(next);
         }
     }
+#if defined(__GNUC__)
+#define PB_PREFETCH(p) __builtin_prefetch((p), 0, 1)
+#else
+#define PB_PREFETCH(p) ((void)0)
+#endif
     struct ParkMillerInt {   // makeRandInt (js/rng.js:8-11); the state is an integer < 2^31, so the JS double
         unsigned long long s;  // arithmetic (s*16807) % 2147483647 is reproduced exactly in 64-bit integers
         explicit ParkMillerInt(double seed) { s = (unsigned long long)(fmod(fabs(floor(seed * 9301.0 + 49297.0)), 2147483646.0) + 1.0); }
         long long operator()(double n) {
-            s = (s * 16807ull) % 2147483647ull;
+            // x mod (2^31 - 1) without a division: fold the high bits twice (x < 2^46), then one conditional subtract
+            unsigned long long x = s * 16807ull;
+            x = (x & 2147483647ull) + (x >> 31);
+            x = (x & 2147483647ull) + (x >> 31);
+            s = x >= 2147483647ull ? x - 2147483647ull : x;
             return (long long)floor(((double)(s - 1) / 2147483646.0) * n);
         }
     };
@@ -136,7 +145,10 @@ struct Elevation {
             const float dn = (float)((double)dist[cur] + 1);
             for (int j = off[cur], e = off[cur + 1]; j < e; j++) {
                 const int nb = adj[j];
-                if (dist[nb] == INFINITY && !(isStop && isStop[nb])) { dist[nb] = dn; queue.push_back(nb); }
+                if (dist[nb] == INFINITY && !(isStop && isStop[nb])) {
+                    dist[nb] = dn; queue.push_back(nb);
+                    PB_PREFETCH(adj + off[nb]);      // the row is read when nb is drawn, typically thousands of steps later
+                }
             }
         }
     }
@@ -250,6 +262,14 @@ struct Elevation {
             for (int j = off[r], e = off[r + 1]; j < e; j++) if (isOcean[adj[j]]) { coastSeeds.add(adj[j]); landCoastSeeds.push_back(r); break; }
         }
         lap("representatives + seeds");
+        // 5a. three of the five randomized fills (:393, 411, 426) read only the sets and the ocean mask: they start now and
+        // overlap the rest of the propagation; the two that need the propagated subduction factor follow below
+        std::vector<float> hd[5];
+        std::thread fill[5];
+        fill[1] = std::thread([&] { distance_field(off, adj, N, ocean.items, coastline.in.data(), seed + 2, hd[1]); });
+        fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
+        fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
+        Joiner joinFills{fill, 5};
         // 3. join the propagation, blend its results (:343-361)
         prop[0].join();
         if (dual) prop[1].join();
@@ -268,15 +288,9 @@ struct Elevation {
         for (int r : mountain.items) if ((double)sub[r] < 0.55) { stressMountain.push_back(r); stop[r] = 1; }
         for (int r : coastline.items) stop[r] = 1;
         for (int r : ocean.items) stop[r] = 1;
-        // 5. five randomized fills (:392-426), each on its own thread; they run concurrently with the capped BFS below
-        std::vector<float> hd[5];
-        std::thread fill[5];
+        // 5b. the two fills that depend on the propagation (:392, 394); all five run concurrently with the capped BFS below
         fill[0] = std::thread([&] { distance_field(off, adj, N, stressMountain, ocean.in.data(), seed + 1, hd[0]); });
-        fill[1] = std::thread([&] { distance_field(off, adj, N, ocean.items, coastline.in.data(), seed + 2, hd[1]); });
         fill[2] = std::thread([&] { distance_field(off, adj, N, coastline.items, stop.data(), seed + 3, hd[2]); });
-        fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
-        fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
-        Joiner joinFills{fill, 5};
 
         // 6. maxStress = p97 of the non-trivial stresses (:443-453)
         double maxStress = 0;
