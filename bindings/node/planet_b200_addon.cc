@@ -226,6 +226,91 @@ napi_value SmoothField(napi_env env, napi_callback_info info) {
     return undefined(env);
 }
 
+// buildSphereFlat(N, jitter, seed) → {numRegions, r_xyz, adjOffset, adjList}; the mesh becomes the retained mesh   js/sphere-mesh.js:174
+napi_value BuildSphere(napi_env env, napi_callback_info info) {
+    Args a(env, info);
+    if (!g_ctx) PB_TRY(env, pb_context_create(0, &g_ctx));
+    const int32_t n = a.i32(0) + 1;
+    void *xyz, *off, *adj;
+    napi_value txyz = new_typed(env, napi_float32_array, 3 * (size_t)n, 4, &xyz);
+    PB_TRY(env, pb_generate_fibonacci_sphere(g_ctx, n - 1, a.num(1), a.num(2), static_cast<float*>(xyz)));
+    if (g_clim) { pb_climate_destroy(g_clim); g_clim = nullptr; }
+    if (g_mesh) { pb_mesh_destroy(g_mesh); g_mesh = nullptr; }
+    PB_TRY(env, pb_mesh_create_from_points(g_ctx, n, static_cast<float*>(xyz), &g_mesh));
+    PB_TRY(env, pb_climate_create(g_mesh, &g_clim));
+    napi_value toff = new_typed(env, napi_int32_array, (size_t)n + 1, 4, &off);
+    napi_value tadj = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_edges(g_mesh), 4, &adj);
+    PB_TRY(env, pb_mesh_get_adjacency(g_mesh, static_cast<int32_t*>(off), static_cast<int32_t*>(adj)));
+    napi_value out, nv; napi_create_object(env, &out); napi_create_double(env, n, &nv);
+    napi_set_named_property(env, out, "numRegions", nv); napi_set_named_property(env, out, "r_xyz", txyz);
+    napi_set_named_property(env, out, "adjOffset", toff); napi_set_named_property(env, out, "adjList", tadj);
+    return out;
+}
+// generateCoarsePlatesFlat(seed, numPlates, numContinents, continentSizeVariety, landCoverage)                       js/coarse-plates.js:19
+//   → {numRegions, adjOffset, adjList, coarse_xyz, coarse_r_plate, seeds, isOcean, pole, omega, density}
+napi_value GenerateCoarsePlates(napi_env env, napi_callback_info info) {
+    Args a(env, info);
+    if (!g_ctx) PB_TRY(env, pb_context_create(0, &g_ctx));
+    const int32_t P = a.i32(1), NC = 20000, n = NC + 1;
+    void *xyz, *rp, *ids, *oc, *pole, *om, *de, *off, *adj;
+    napi_value txyz = new_typed(env, napi_float32_array, 3 * (size_t)n, 4, &xyz), trp = new_typed(env, napi_int32_array, n, 4, &rp);
+    napi_value tids = new_typed(env, napi_int32_array, P, 4, &ids), toc = new_typed(env, napi_uint8_array, P, 1, &oc);
+    napi_value tpole = new_typed(env, napi_float64_array, 3 * (size_t)P, 8, &pole), tom = new_typed(env, napi_float64_array, P, 8, &om);
+    napi_value tde = new_typed(env, napi_float64_array, P, 8, &de);
+    pb_plate_table_out t{P, 0, static_cast<int32_t*>(ids), static_cast<uint8_t*>(oc), static_cast<double*>(pole), static_cast<double*>(om),
+                         static_cast<double*>(de)};
+    pb_mesh* coarse = nullptr;
+    PB_TRY(env, pb_generate_coarse_plates(g_ctx, a.num(0), P, a.i32(2), a.num(3, 0.0), a.num(4, 0.3), NC, &coarse, static_cast<float*>(xyz),
+                                          static_cast<int32_t*>(rp), &t));
+    napi_value toff = new_typed(env, napi_int32_array, (size_t)n + 1, 4, &off);
+    napi_value tadj = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_edges(coarse), 4, &adj);
+    const pb_status st = pb_mesh_get_adjacency(coarse, static_cast<int32_t*>(off), static_cast<int32_t*>(adj));
+    pb_mesh_destroy(coarse);
+    PB_TRY(env, st);
+    napi_value out, nv, np; napi_create_object(env, &out); napi_create_double(env, n, &nv); napi_create_double(env, t.n, &np);
+    const char* names[] = {"adjOffset", "adjList", "coarse_xyz", "coarse_r_plate", "seeds", "isOcean", "pole", "omega", "density"};
+    napi_value vals[] = {toff, tadj, txyz, trp, tids, toc, tpole, tom, tde};
+    for (int k = 0; k < 9; k++) napi_set_named_property(env, out, names[k], vals[k]);
+    napi_set_named_property(env, out, "numRegions", nv); napi_set_named_property(env, out, "numPlates", np);
+    return out;
+}
+// projectCoarsePlatesFlat(numCoarse, cAdjOffset, cAdjList, coarse_xyz, coarse_r_plate, seed, numPlates|null) → Int32Array   js/coarse-plates.js:51
+napi_value ProjectCoarsePlates(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    void* d;
+    napi_value out = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_regions(g_mesh), 4, &d);
+    PB_TRY(env, pb_project_coarse_plates(g_mesh, a.i32(0), a.typed<int32_t>(1), a.typed<int32_t>(2), a.typed<float>(3), a.typed<int32_t>(4),
+                                         a.num(5), a.present(6) ? a.i32(6) : -1, static_cast<int32_t*>(d)));
+    return out;
+}
+// smoothAndReconnectPlatesFlat(r_plate, plateSeeds:Int32Array, numPasses)  in place                                 js/plates.js:241
+napi_value SmoothAndReconnectPlates(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    size_t ns = 0;
+    const int32_t* seeds = a.typed<int32_t>(1, &ns);
+    PB_TRY(env, pb_smooth_and_reconnect_plates(g_mesh, a.typed<int32_t>(0), seeds, (int32_t)ns, a.i32(2)));
+    return undefined(env);
+}
+// buildSuperPlatesFlat(r_plate, ids, isOcean, pole, omega, density) → {r_superPlate, numSuperPlates, pole, omega, isOcean, density}   js/super-plates.js:16
+napi_value BuildSuperPlates(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    size_t P = 0;
+    const int32_t* ids = a.typed<int32_t>(1, &P);
+    pb_plate_table t{(int32_t)P, ids, a.typed<uint8_t>(2), a.typed<double>(3), a.typed<double>(4), a.typed<double>(5)};
+    const size_t cap = P < 2 ? 2 : P;
+    void *rs, *pole, *om, *oc, *de;
+    napi_value trs = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_regions(g_mesh), 4, &rs);
+    napi_value tpole = new_typed(env, napi_float64_array, 3 * cap, 8, &pole), tom = new_typed(env, napi_float64_array, cap, 8, &om);
+    napi_value toc = new_typed(env, napi_uint8_array, cap, 1, &oc), tde = new_typed(env, napi_float64_array, cap, 8, &de);
+    pb_super_plate_table sp{(int32_t)cap, 0, static_cast<double*>(pole), static_cast<double*>(om), static_cast<uint8_t*>(oc), static_cast<double*>(de)};
+    PB_TRY(env, pb_build_super_plates(g_mesh, a.typed<int32_t>(0), &t, static_cast<int32_t*>(rs), &sp));
+    napi_value out, nv; napi_create_object(env, &out); napi_create_double(env, sp.numSuperPlates, &nv);
+    napi_set_named_property(env, out, "r_superPlate", trs); napi_set_named_property(env, out, "numSuperPlates", nv);
+    napi_set_named_property(env, out, "pole", tpole); napi_set_named_property(env, out, "omega", tom);
+    napi_set_named_property(env, out, "isOcean", toc); napi_set_named_property(env, out, "density", tde);
+    return out;
+}
+
 }  // namespace
 
 NAPI_MODULE_INIT() {
@@ -247,6 +332,11 @@ NAPI_MODULE_INIT() {
         {"classifyKoppenFlat", nullptr, ClassifyKoppen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"getClimateField", nullptr, GetClimateField, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"smoothField", nullptr, SmoothField, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"buildSphereFlat", nullptr, BuildSphere, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"generateCoarsePlatesFlat", nullptr, GenerateCoarsePlates, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"projectCoarsePlatesFlat", nullptr, ProjectCoarsePlates, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"smoothAndReconnectPlatesFlat", nullptr, SmoothAndReconnectPlates, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"buildSuperPlatesFlat", nullptr, BuildSuperPlates, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
     return exports;

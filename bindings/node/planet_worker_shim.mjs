@@ -20,6 +20,51 @@ export const sharpenRidges = native.sharpenRidges;
 export const applySoilCreep = native.applySoilCreep;
 export const smoothField = native.smoothField;
 
+// buildSphere(N, jitter, rng): the addon needs the seed the caller's rng was built from — pass {seed} (makeRng(seed), :146).
+// Returns {mesh, r_xyz} like js/sphere-mesh.js:174; the mesh is also retained for the stage functions below.
+export function buildSphere(N, jitter, rng) {
+  const r = native.buildSphereFlat(N, jitter, rng.seed);
+  return { mesh: { numRegions: r.numRegions, adjOffset: r.adjOffset, adjList: r.adjList }, r_xyz: r.r_xyz };
+}
+
+// generateCoarsePlates(seed, numPlates, numContinents, continentSizeVariety, landCoverage)      js/coarse-plates.js:19
+export function generateCoarsePlates(seed, numPlates, numContinents, continentSizeVariety = 0, landCoverage = 0.3) {
+  const r = native.generateCoarsePlatesFlat(seed, numPlates, numContinents, continentSizeVariety, landCoverage);
+  const seeds = Array.from(r.seeds.subarray(0, r.numPlates));
+  const coarsePlateVec = {}, coarsePlateIsOcean = new Set();
+  seeds.forEach((pid, k) => {
+    coarsePlateVec[pid] = { pole: Array.from(r.pole.subarray(3 * k, 3 * k + 3)), omega: r.omega[k] };
+    if (r.isOcean[k]) coarsePlateIsOcean.add(pid);
+  });
+  return { coarseMesh: { numRegions: r.numRegions, adjOffset: r.adjOffset, adjList: r.adjList }, coarse_xyz: r.coarse_xyz,
+           coarse_r_plate: r.coarse_r_plate, coarsePlateSeeds: new Set(seeds), coarsePlateVec, coarsePlateIsOcean };
+}
+export function projectCoarsePlates(mesh, r_xyz, coarseMesh, coarse_xyz, coarse_r_plate, seed, numPlates) {
+  return native.projectCoarsePlatesFlat(coarseMesh.numRegions, coarseMesh.adjOffset, coarseMesh.adjList, coarse_xyz, coarse_r_plate,
+                                        seed, numPlates ?? null);
+}
+export function smoothAndReconnectPlates(mesh, r_plate, plateSeeds, numPasses) {
+  native.smoothAndReconnectPlatesFlat(r_plate, Int32Array.from(plateSeeds), numPasses);
+}
+export function buildSuperPlates(mesh, r_plate, plateSeeds, plateVec, plateIsOcean, plateDensity) {
+  const ids = Int32Array.from(plateSeeds), n = ids.length;
+  const isOcean = new Uint8Array(n), pole = new Float64Array(3 * n).fill(NaN), omega = new Float64Array(n), dens = new Float64Array(n).fill(NaN);
+  ids.forEach((pid, k) => {
+    isOcean[k] = plateIsOcean.has(pid) ? 1 : 0;
+    const pv = plateVec[pid];
+    if (pv && pv.pole) { pole.set(pv.pole, 3 * k); omega[k] = pv.omega; }
+    if (plateDensity[pid] !== undefined) dens[k] = plateDensity[pid];
+  });
+  const r = native.buildSuperPlatesFlat(r_plate, ids, isOcean, pole, omega, dens);
+  const superPlateVec = {}, superPlateIsOcean = new Set(), superPlateDensity = {};
+  for (let sp = 0; sp < r.numSuperPlates; sp++) {
+    superPlateVec[sp] = { pole: Array.from(r.pole.subarray(3 * sp, 3 * sp + 3)), omega: r.omega[sp] };
+    if (r.isOcean[sp]) superPlateIsOcean.add(sp);
+    superPlateDensity[sp] = r.density[sp];
+  }
+  return { r_superPlate: r.r_superPlate, superPlateVec, superPlateIsOcean, superPlateDensity, numSuperPlates: r.numSuperPlates };
+}
+
 // runPostProcessing is module-private in planet-worker.js (:40-102); the worker may call this instead.
 export function runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot) {
   const r = native.runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot ?? null);
