@@ -51,6 +51,23 @@ def compute():
               "r_temperature_summer", "r_temperature_winter"):
         out["climate." + k] = sha(oc.get(k))
     out["climate.r_coastDistLand"] = sha(oc.get("r_coastDistLand", np.int32))
+    # plate pipeline (coarse stage on a 4 000-region coarse mesh, projection, smoothing, super plates)
+    cp = oracle.generate_coarse_plates(42, 24, 3, 0.5, 0.3, n_coarse=4000)
+    out["plates.coarse_xyz"] = sha(cp["coarse_xyz"])
+    out["plates.coarse_adjList"] = sha(cp["coarseMesh"].adjList)
+    out["plates.coarse_r_plate"] = sha(cp["coarse_r_plate"])
+    out["plates.seeds"] = sha(np.asarray(cp["coarsePlateSeeds"], np.int32))
+    out["plates.poles"] = sha(np.asarray([cp["coarsePlateVec"][s]["pole"] + [cp["coarsePlateVec"][s]["omega"]] for s in cp["coarsePlateSeeds"]]))
+    out["plates.isOcean"] = sha(np.asarray([s in cp["coarsePlateIsOcean"] for s in cp["coarsePlateSeeds"]], np.uint8))
+    rp = oracle.project_coarse_plates(mesh, xyz, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], 42, 24)
+    out["plates.projected"] = sha(rp)
+    oracle.smooth_and_reconnect_plates(mesh, rp, cp["coarsePlateSeeds"], 3)
+    out["plates.smoothed"] = sha(rp)
+    table = {s: dict(isOcean=s in cp["coarsePlateIsOcean"], pole=tuple(cp["coarsePlateVec"][s]["pole"]),
+                     omega=cp["coarsePlateVec"][s]["omega"], density=2.5 + 0.01 * i) for i, s in enumerate(cp["coarsePlateSeeds"])}
+    rs, spt = oracle.build_super_plates(mesh, rp, table)
+    out["plates.r_superPlate"] = sha(rs)
+    out["plates.superTable"] = sha(np.asarray([list(spt[k]["pole"]) + [spt[k]["omega"], spt[k]["density"], float(spt[k]["isOcean"])] for k in sorted(spt)]))
     return out
 
 
