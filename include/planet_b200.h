@@ -267,6 +267,17 @@ pb_status pb_triangulate_sphere(pb_context* ctx, int32_t numRegions, const float
 pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
 pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* adjOffset, int32_t* adjList);
 
+/* ---- triangles: what the worker's `done` / `reapplyDone` / `editDone` replies carry for the renderer ----------------
+ * pb_mesh_get_triangles: SphereMesh.triangles / .halfedges (js/sphere-mesh.js:94-100) of the mesh, 3*numTriangles ints
+ * each, in the canonical numbering (csrc/pb_meshgen.h); numTriangles = 2*numRegions - 4.
+ * pb_generate_triangle_centers replaces generateTriangleCenters(mesh, r_xyz) (js/sphere-mesh.js:206-219);
+ * pb_compute_triangle_elevations replaces computeTriangleElevations(mesh, r_elevation) (js/planet-worker.js:29-37).
+ * Arrays follow the context's pointer mode. */
+int32_t pb_mesh_num_triangles(const pb_mesh* mesh);
+pb_status pb_mesh_get_triangles(pb_mesh* mesh, int32_t* triangles, int32_t* halfedges);
+pb_status pb_generate_triangle_centers(pb_mesh* mesh, float* t_xyz);
+pb_status pb_compute_triangle_elevations(pb_mesh* mesh, const float* r_elevation, float* t_elevation);
+
 /* ---- cell-range shards with device-side halo exchange (no reference counterpart: the reference is one thread) ----
  * One process per GPU.  `mesh` is the rank's LOCAL mesh: owned cells [0, nOwn) followed by the halo cells its rows
  * read (halo rows empty), see planet_heightmap_generation_b200/sharded.py.  For every peer the caller gives the

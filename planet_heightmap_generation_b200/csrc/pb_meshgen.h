@@ -380,3 +380,109 @@ struct SphereTriangulator {
 };
 
 }  // namespace pb
+
+// ---- triangles / half-edges of a mesh from its CSR rows (SphereMesh.triangles / .halfedges, js/sphere-mesh.js:94-100) ----
+// A row lists a region's neighbours clockwise (seen from outside), so the counter-clockwise triangle between two
+// consecutive entries is (r, row[k+1], row[k]).  In the canonical numbering every triangle starts at its smallest
+// vertex and triangles are in lexicographic order: region r owns the triangles in which it is the smallest vertex, sorted
+// by (second, third) — a count pass, a scan and a fill pass give `triangles`; the twin of side a→b is found in the block
+// of the smallest vertex of the triangle on the other side of the edge.
+namespace pb {
+
+struct TriCountK {
+    Csr g; int* cnt;
+    PB_DEV void operator()(int r) const {
+        const int s = g.off[r], d = g.off[r + 1] - s;
+        int c = 0;
+        for (int k = 0; k < d; k++) { const int b = g.adj[s + (k + 1 == d ? 0 : k + 1)], cc = g.adj[s + k]; if (r < b && r < cc) c++; }
+        cnt[r] = c;
+    }
+};
+struct TriFillK {
+    Csr g; const int* start; int* tri;
+    PB_DEV void operator()(int r) const {
+        const int s = g.off[r], d = g.off[r + 1] - s;
+        int bs[32], cs[32], n = 0;
+        for (int k = 0; k < d; k++) {
+            const int b = g.adj[s + (k + 1 == d ? 0 : k + 1)], c = g.adj[s + k];
+            if (!(r < b && r < c)) continue;
+            int at = n++;
+            while (at > 0 && (bs[at - 1] > b || (bs[at - 1] == b && cs[at - 1] > c))) { bs[at] = bs[at - 1]; cs[at] = cs[at - 1]; at--; }
+            bs[at] = b; cs[at] = c;
+        }
+        int* out = tri + 3 * (size_t)start[r];
+        for (int i = 0; i < n; i++) { out[3 * i] = r; out[3 * i + 1] = bs[i]; out[3 * i + 2] = cs[i]; }
+    }
+};
+struct HalfedgeK {
+    Csr g; const int* start; const int* tri; int* half; int* bad;
+    PB_DEV void operator()(int side) const {
+        const int t = side / 3, e = side - 3 * t;
+        const int a = tri[3 * t + e], b = tri[3 * t + (e == 2 ? 0 : e + 1)];
+        // the third vertex of the triangle on the other side of a→b: the entry after b in a's (clockwise) row
+        const int s = g.off[a], d = g.off[a + 1] - s;
+        int p = -1;
+        for (int k = 0; k < d; k++) if (g.adj[s + k] == b) { p = k; break; }
+        if (p < 0) { atomic_add(bad, 1); half[side] = -1; return; }
+        const int x = g.adj[s + (p + 1 == d ? 0 : p + 1)];
+        // that triangle is (a, x, b) counter-clockwise; rotate to its smallest vertex and look it up in that vertex's block
+        int v0 = a, v1 = x, v2 = b;
+        if (x < a && x < b) { v0 = x; v1 = b; v2 = a; } else if (b < a && b < x) { v0 = b; v1 = a; v2 = x; }
+        int found = -1;
+        for (int u = start[v0]; u < start[v0 + 1]; u++) if (tri[3 * u + 1] == v1 && tri[3 * u + 2] == v2) { found = u; break; }
+        if (found < 0) { atomic_add(bad, 1); half[side] = -1; return; }
+        const int pos = v0 == b ? 0 : (v1 == b ? 1 : 2);          // the twin side starts at b
+        half[side] = 3 * found + pos;
+    }
+};
+// generateTriangleCenters (js/sphere-mesh.js:206-219) and computeTriangleElevations (js/planet-worker.js:29-37)
+struct TriCentersK {
+    const int* tri; const float* xyz; float* t_xyz;
+    PB_DEV void operator()(int t) const {
+        const int a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        for (int k = 0; k < 3; k++) t_xyz[3 * t + k] = (float)((((double)xyz[3 * a + k] + (double)xyz[3 * b + k]) + (double)xyz[3 * c + k]) / 3);
+    }
+};
+struct TriElevationK {
+    const int* tri; const float* elev; float* t_elev;
+    PB_DEV void operator()(int t) const {
+        t_elev[t] = (float)((((double)elev[tri[3 * t]] + (double)elev[tri[3 * t + 1]]) + (double)elev[tri[3 * t + 2]]) / 3);
+    }
+};
+
+struct MeshTriangles {
+    DevBuf<int> cnt, start, tri, half, flag;
+    DevBuf<uint8_t> scanTemp;
+    int T = 0;
+    // builds (once per mesh) the device copies; tri / half are 3T ints
+    void build(const Exec& ex, Csr g, int N) {
+        if (T) return;
+        cnt.ensure((size_t)N + 1); start.ensure((size_t)N + 1); flag.ensure(2);
+        dev_memset(cnt.p + N, 0, sizeof(int), ex.stream);
+        dev_memset(flag.p, 0, 2 * sizeof(int), ex.stream);
+        ex.for_each(N, TriCountK{g, cnt.p});
+        launch_stats().launches++;
+#if PB_CUDA
+        size_t bytes = 0;
+        PB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, start.p, N + 1, ex.stream));
+        scanTemp.ensure(bytes);
+        PB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scanTemp.p, bytes, cnt.p, start.p, N + 1, ex.stream));
+#else
+        { int acc = 0; for (int i = 0; i <= N; i++) { const int v = cnt.p[i]; start.p[i] = acc; acc += v; } }
+#endif
+        int total = 0;
+        dev_copy(&total, start.p + N, sizeof(int), 1, ex.stream);
+        stream_sync(ex.stream);
+        if (total != 2 * N - 4) throw Error("mesh is not a closed triangulated sphere: " + std::to_string(total) + " triangles for " + std::to_string(N) + " regions");
+        tri.ensure(3 * (size_t)total); half.ensure(3 * (size_t)total);
+        ex.for_each(N, TriFillK{g, start.p, tri.p});
+        ex.for_each(3 * total, HalfedgeK{g, start.p, tri.p, half.p, flag.p});
+        int bad = 0;
+        dev_copy(&bad, flag.p, sizeof(int), 1, ex.stream);
+        stream_sync(ex.stream);
+        if (bad) throw Error("mesh rows are not consistent circulations: " + std::to_string(bad) + " sides without a twin");
+        T = total;
+    }
+};
+
+}  // namespace pb

@@ -46,6 +46,8 @@ struct pb_mesh {
     pb::Mesh m;
     std::unique_ptr<pb::Elevation> elevation;
     std::unique_ptr<pb::Plates> plates;
+    pb::MeshTriangles triangles;
+    pb::DevBuf<float> sTriOut;
     pb::DevBuf<int> sPlateIO, sSuperIO;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
@@ -458,6 +460,46 @@ pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_
             superOut->omega[sp] = o.omega[sp]; superOut->isOcean[sp] = o.isOcean[sp]; superOut->density[sp] = o.density[sp];
         }
         m.arg_back(r_superPlate, dSuper, (size_t)m.N);
+        m.finish();
+    });
+}
+
+// ---- triangles (render-side consumers of the mesh) ------------------------------------------------------------------
+int32_t pb_mesh_num_triangles(const pb_mesh* mesh) { return mesh ? 2 * mesh->m.N - 4 : 0; }
+pb_status pb_mesh_get_triangles(pb_mesh* mesh, int32_t* triangles, int32_t* halfedges) {
+    return guard([&] {
+        need(mesh && triangles && halfedges, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        mesh->triangles.build(m.ex(), m.csr(), m.N);
+        const size_t n3 = 3 * (size_t)mesh->triangles.T;
+        const int kind = m.hostMode() ? 1 : 2;
+        pb::dev_copy(triangles, mesh->triangles.tri.p, sizeof(int) * n3, kind, m.ex().stream);
+        pb::dev_copy(halfedges, mesh->triangles.half.p, sizeof(int) * n3, kind, m.ex().stream);
+        m.finish();
+    });
+}
+pb_status pb_generate_triangle_centers(pb_mesh* mesh, float* t_xyz) {
+    return guard([&] {
+        need(mesh && t_xyz, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        mesh->triangles.build(m.ex(), m.csr(), m.N);
+        const size_t T = (size_t)mesh->triangles.T;
+        float* d = m.arg_out(t_xyz, 3 * T, mesh->sTriOut);
+        m.ex().for_each((int)T, pb::TriCentersK{mesh->triangles.tri.p, m.xyz.p, d});
+        m.arg_back(t_xyz, d, 3 * T);
+        m.finish();
+    });
+}
+pb_status pb_compute_triangle_elevations(pb_mesh* mesh, const float* r_elevation, float* t_elevation) {
+    return guard([&] {
+        need(mesh && r_elevation && t_elevation, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        mesh->triangles.build(m.ex(), m.csr(), m.N);
+        const size_t T = (size_t)mesh->triangles.T;
+        const float* e = m.arg_in(r_elevation, (size_t)m.N, m.sElev);
+        float* d = m.arg_out(t_elevation, T, mesh->sTriOut);
+        m.ex().for_each((int)T, pb::TriElevationK{mesh->triangles.tri.p, e, d});
+        m.arg_back(t_elevation, d, T);
         m.finish();
     });
 }

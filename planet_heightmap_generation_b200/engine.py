@@ -101,6 +101,10 @@ class DeviceMesh:
         return self
 
     def close(self):
+        st = getattr(self, "_climate", None)
+        if st is not None:                # the climate state points into the mesh: release it first
+            st.close()
+            self._climate = None
         if getattr(self, "_mesh", None):
             self.lib.dll.pb_mesh_destroy(self._mesh)
             self._mesh = None
@@ -173,6 +177,35 @@ class DeviceMesh:
         return int(self.lib.dll.pb_launch_count())
 
     # ---- mesh primitives ------------------------------------------------------------------------------
+    @property
+    def numTriangles(self) -> int:
+        return 2 * self.numRegions - 4
+
+    def trianglesAndHalfedges(self):
+        """SphereMesh.triangles / .halfedges (js/sphere-mesh.js:94-100), canonical numbering, as numpy int32 arrays."""
+        t = np.empty(3 * self.numTriangles, np.int32)
+        h = np.empty(3 * self.numTriangles, np.int32)
+        self._begin(t, h)
+        self.lib.check(self.lib.dll.pb_mesh_get_triangles(self._mesh, t.ctypes.data, h.ctypes.data))
+        return t, h
+
+    def generateTriangleCenters(self, out=None):
+        """generateTriangleCenters(mesh, r_xyz) (js/sphere-mesh.js:206-219)"""
+        if out is None:
+            out = np.empty(3 * self.numTriangles, np.float32)
+        self._begin(out)
+        self.lib.check(self.lib.dll.pb_generate_triangle_centers(self._mesh, self._ptr(out, "f32", 3 * self.numTriangles, "t_xyz")))
+        return out
+
+    def computeTriangleElevations(self, r_elevation, out=None):
+        """computeTriangleElevations(mesh, r_elevation) (js/planet-worker.js:29-37)"""
+        if out is None:
+            out = self._new(r_elevation, "f32", self.numTriangles)
+        self._begin(r_elevation, out)
+        self.lib.check(self.lib.dll.pb_compute_triangle_elevations(
+            self._mesh, self._ptr(r_elevation, "f32", self.numRegions, "r_elevation"), self._ptr(out, "f32", self.numTriangles, "t_elevation")))
+        return out
+
     def generateFibonacciSphere(self, N: int, jitter: float, seed: float, out=None):
         """generateFibonacciSphere + the pole vertex (js/sphere-mesh.js:9-37, 179-183): 3·(N+1) floats."""
         if out is None:

@@ -122,3 +122,28 @@ def test_million_cell_mesh_on_device(cuda_lib):
     mesh, _ = _hull(xyz)
     _check_same(dm, mesh)
     dm.close()
+
+
+@pytest.mark.parametrize("n,seed", [(30, 3.0), (3000, 42.0), (20000, 7.0)])
+def test_triangles_and_halfedges_match_hull(backend, n, seed):
+    """SphereMesh.triangles / .halfedges rebuilt on the device from the CSR rows, triangle centres and triangle
+    elevations (what the worker's replies carry for the renderer) against the hull checker."""
+    xyz = sphere_points(n, 0.75, seed)
+    mesh, xyz = _hull(xyz)
+    dm = DeviceMesh.from_points(xyz, lib=backend)
+    tri, half = dm.trianglesAndHalfedges()
+    assert dm.numTriangles == mesh.numTriangles
+    assert np.array_equal(tri, mesh.triangles) and np.array_equal(half, mesh.halfedges)
+    # half-edge invariants (js/sphere-mesh.js: s_end_r(s) == s_begin_r(halfedges[s]))
+    nxt = np.where(np.arange(tri.size) % 3 == 2, np.arange(tri.size) - 2, np.arange(tri.size) + 1)
+    assert np.array_equal(half[half], np.arange(tri.size)) and np.array_equal(tri[nxt], tri[half])
+    p = xyz.reshape(-1, 3).astype(np.float64)
+    t = tri.reshape(-1, 3)
+    want_c = (((p[t[:, 0]] + p[t[:, 1]]) + p[t[:, 2]]) / 3).astype(np.float32).reshape(-1)
+    assert (dm.generateTriangleCenters().view(np.uint32) == want_c.view(np.uint32)).all()
+    from planet_heightmap_generation_b200.sphere import synthetic_elevation
+    elev = synthetic_elevation(xyz, 5, 0.3)
+    e = elev.astype(np.float64)
+    want_e = (((e[t[:, 0]] + e[t[:, 1]]) + e[t[:, 2]]) / 3).astype(np.float32)
+    assert (dm.computeTriangleElevations(elev).view(np.uint32) == want_e.view(np.uint32)).all()
+    dm.close()
