@@ -267,6 +267,19 @@ pb_status pb_triangulate_sphere(pb_context* ctx, int32_t numRegions, const float
 pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
 pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* adjOffset, int32_t* adjList);
 
+/* ---- importHeightmap pieces (js/planet-worker.js:682-831) -------------------------------------------------------------
+ * pb_sample_heightmap replaces sampleHeightmap(mesh, r_xyz, imageData, imgW, imgH) (:715-727, with sampleBilinear :682 and
+ * grayscaleToElevation :705): grayscale is a host array of width*height bytes (equirectangular, 0 = ocean).
+ * pb_derive_synthetic_plates replaces deriveSyntheticPlates (:733-769): r_plate[r] = lowest region id of r's connected land
+ * mass / ocean basin; plateSeeds are the ids with r_plate[r] == r in ascending order, a plate is oceanic iff
+ * r_elevation[seed] <= 0, plateVec is all-zero.
+ * pb_classify_imported_regions gives the mountain_r / coastline_r / ocean_r masks of :811-831.
+ * Per-region arrays follow the context's pointer mode. */
+pb_status pb_sample_heightmap(pb_mesh* mesh, const uint8_t* grayscale, int32_t width, int32_t height, float* r_elevation);
+pb_status pb_derive_synthetic_plates(pb_mesh* mesh, const float* r_elevation, int32_t* r_plate);
+pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, uint8_t* mountain_r, uint8_t* coastline_r,
+                                       uint8_t* ocean_r);
+
 /* ---- triangles: what the worker's `done` / `reapplyDone` / `editDone` replies carry for the renderer ----------------
  * pb_mesh_get_triangles: SphereMesh.triangles / .halfedges (js/sphere-mesh.js:94-100) of the mesh, 3*numTriangles ints
  * each, in the canonical numbering (csrc/pb_meshgen.h); numTriangles = 2*numRegions - 4.

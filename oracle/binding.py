@@ -375,3 +375,27 @@ def generate_coarse_plates(seed, num_plates, num_continents, continent_size_vari
     return dict(coarseMesh=cmesh, coarse_xyz=cxyz, coarse_r_plate=r_plate, coarsePlateSeeds=ids,
                 coarsePlateVec={s: {"pole": [float(v) for v in pole[3 * i:3 * i + 3]], "omega": float(omega[i])} for i, s in enumerate(ids)},
                 coarsePlateIsOcean={s for i, s in enumerate(ids) if oc[i]})
+
+
+# ---- importHeightmap pieces (js/planet-worker.js:682-831) -------------------------------------------------------------
+def sample_heightmap(mesh, xyz, grayscale, width, height):
+    px = np.ascontiguousarray(grayscale, np.uint8)
+    out = np.empty(mesh.numRegions, np.float32)
+    lib().orc_sample_heightmap(C.c_int(mesh.numRegions), _p(np.ascontiguousarray(xyz, np.float32), C.c_float), _p(px, C.c_uint8),
+                               C.c_int(width), C.c_int(height), _p(out, C.c_float))
+    return out
+
+
+def derive_synthetic_plates(mesh, elev):
+    """→ (r_plate, plateSeeds in Set order, plateIsOcean set)"""
+    out = np.empty(mesh.numRegions, np.int32)
+    lib().orc_derive_synthetic_plates(*_mesh_args(mesh), _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(out, C.c_int32))
+    seeds = [int(r) for r in np.nonzero(out == np.arange(mesh.numRegions))[0]]
+    return out, seeds, {s for s in seeds if elev[s] <= 0}
+
+
+def classify_imported(mesh, elev):
+    m, c, o = (np.empty(mesh.numRegions, np.uint8) for _ in range(3))
+    lib().orc_classify_imported(*_mesh_args(mesh), _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(m, C.c_uint8), _p(c, C.c_uint8),
+                                _p(o, C.c_uint8))
+    return m, c, o

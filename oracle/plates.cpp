@@ -259,9 +259,70 @@ int build_super_plates(int N, const int32_t* off, const int32_t* adj, const int3
     return nSP;
 }
 
+// js/planet-worker.js:682-727 (sampleBilinear, grayscaleToElevation, sampleHeightmap)
+void sample_heightmap(int N, const float* xyz, const uint8_t* pixels, int imgW, int imgH, float* r_elevation) {
+    for (int r = 0; r < N; r++) {
+        const double x = xyz[3 * r], y = xyz[3 * r + 1], z = xyz[3 * r + 2];
+        const double lat = pb_asin(js::max(-1, js::min(1, y)));
+        const double lon = pb_atan2(x, z);
+        const double px = (lon / PB_PI + 1) * 0.5 * imgW;
+        double py = (0.5 - lat / PB_PI) * imgH;
+        py = js::max(0, js::min(py, imgH - 1));
+        const double x0 = std::floor(px), y0 = std::floor(py);
+        const double x1 = std::fmod(x0 + 1, (double)imgW);
+        const double y1 = js::min(y0 + 1, imgH - 1);
+        const double fx = px - x0, fy = py - y0;
+        const double xw = std::fmod(std::fmod(x0, (double)imgW) + imgW, (double)imgW);
+        const double v00 = pixels[(size_t)(y0 * imgW + xw)], v10 = pixels[(size_t)(y0 * imgW + x1)];
+        const double v01 = pixels[(size_t)(y1 * imgW + xw)], v11 = pixels[(size_t)(y1 * imgW + x1)];
+        const double gray = v00 * (1 - fx) * (1 - fy) + v10 * fx * (1 - fy) + v01 * (1 - fx) * fy + v11 * fx * fy;
+        r_elevation[r] = js::f32(gray < 1 ? -0.5 : std::sqrt((gray - 1) / 254));
+    }
+}
+
+// js/planet-worker.js:733-769 (deriveSyntheticPlates): one plate per connected land mass / ocean basin, id = first region met
+void derive_synthetic_plates(int N, const int32_t* off, const int32_t* adj, const float* elev, int32_t* r_plate) {
+    for (int r = 0; r < N; r++) r_plate[r] = -1;
+    std::vector<int> queue;
+    for (int r = 0; r < N; r++) {
+        if (r_plate[r] >= 0) continue;
+        const bool isOcean = elev[r] <= 0;
+        r_plate[r] = r;
+        queue.assign(1, r);
+        for (size_t head = 0; head < queue.size(); head++) {
+            const int cur = queue[head];
+            for (int ni = off[cur], e = off[cur + 1]; ni < e; ni++) {
+                const int nb = adj[ni];
+                if (r_plate[nb] >= 0) continue;
+                if ((elev[nb] <= 0) == isOcean) { r_plate[nb] = r; queue.push_back(nb); }
+            }
+        }
+    }
+}
+
+// js/planet-worker.js:811-831: region classes of an imported heightmap
+void classify_imported(int N, const int32_t* off, const int32_t* adj, const float* elev, uint8_t* mountain, uint8_t* coastline, uint8_t* ocean) {
+    for (int r = 0; r < N; r++) {
+        mountain[r] = coastline[r] = ocean[r] = 0;
+        if (elev[r] <= 0) ocean[r] = 1;
+        else if ((double)elev[r] > 0.5) mountain[r] = 1;
+        if (elev[r] > 0)
+            for (int ni = off[r], e = off[r + 1]; ni < e; ni++) if (elev[adj[ni]] <= 0) { coastline[r] = 1; break; }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+void orc_sample_heightmap(int N, const float* xyz, const uint8_t* pixels, int imgW, int imgH, float* r_elevation) {
+    sample_heightmap(N, xyz, pixels, imgW, imgH, r_elevation);
+}
+void orc_derive_synthetic_plates(int N, const int32_t* off, const int32_t* adj, const float* elev, int32_t* r_plate) {
+    derive_synthetic_plates(N, off, adj, elev, r_plate);
+}
+void orc_classify_imported(int N, const int32_t* off, const int32_t* adj, const float* elev, uint8_t* mountain, uint8_t* coastline, uint8_t* ocean) {
+    classify_imported(N, off, adj, elev, mountain, coastline, ocean);
+}
 void orc_project_coarse_plates(int N, const float* r_xyz, int NC, const int32_t* cOff, const int32_t* cAdj, const float* coarse_xyz,
                                const int32_t* coarse_r_plate, double seed, int numPlates, int32_t* r_plate) {
     project_coarse_plates(N, r_xyz, NC, cOff, cAdj, coarse_xyz, coarse_r_plate, seed, numPlates, r_plate);

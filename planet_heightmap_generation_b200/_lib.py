@@ -70,6 +70,9 @@ SYMBOLS = {
     "pb_smooth_and_reconnect_plates": (C.c_int, [_vp, _vp, _vp, _i32, _i32]),
     "pb_build_super_plates": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_generate_coarse_plates": (C.c_int, [_vp, C.c_double, _i32, _i32, C.c_double, C.c_double, _i32, C.POINTER(_vp), _vp, _vp, _vp]),
+    "pb_sample_heightmap": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "pb_derive_synthetic_plates": (C.c_int, [_vp, _vp, _vp]),
+    "pb_classify_imported_regions": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_mesh_num_triangles": (_i32, [_vp]),
     "pb_mesh_get_triangles": (C.c_int, [_vp, _vp, _vp]),
     "pb_generate_triangle_centers": (C.c_int, [_vp, _vp]),

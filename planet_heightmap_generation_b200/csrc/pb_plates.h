@@ -206,6 +206,48 @@ struct SuperGatherK {
     PB_DEV void operator()(int r) const { r_super[r] = plateToSuper[pidx[plate[r]]]; }
 };
 
+// ---- importHeightmap (js/planet-worker.js:682-831) ---------------------------------------------------------------------
+struct SampleHeightmapK {
+    const float* xyz; const uint8_t* px; int W, H; float* elev;
+    PB_DEV void operator()(int r) const {
+        const double x = xyz[3 * r], y = xyz[3 * r + 1], z = xyz[3 * r + 2];
+        const double lat = pb_asin(y < -1 ? -1 : (y > 1 ? 1 : y));
+        const double lon = pb_atan2(x, z);
+        const double fxp = (lon / PB_PI + 1) * 0.5 * W;
+        double fyp = (0.5 - lat / PB_PI) * H;
+        if (fyp > H - 1) fyp = H - 1;
+        if (fyp < 0) fyp = 0;
+        const double x0 = floor(fxp), y0 = floor(fyp);
+        long long ix0 = (long long)x0 % W; if (ix0 < 0) ix0 += W;             // ((x0 % W) + W) % W
+        const long long ix1 = (long long)(x0 + 1) % W;                           // px >= 0, so no negative remainder here
+        const long long iy0 = (long long)y0, iy1 = iy0 + 1 > H - 1 ? H - 1 : iy0 + 1;
+        const double fx = fxp - x0, fy = fyp - y0;
+        const double v00 = px[iy0 * W + ix0], v10 = px[iy0 * W + ix1], v01 = px[iy1 * W + ix0], v11 = px[iy1 * W + ix1];
+        const double gray = v00 * (1 - fx) * (1 - fy) + v10 * fx * (1 - fy) + v01 * (1 - fx) * fy + v11 * fx * fy;
+        elev[r] = (float)(gray < 1 ? -0.5 : sqrt((gray - 1) / 254));
+    }
+};
+// land / ocean label per region; components of equal label are the synthetic plates, named by their lowest id
+struct LandOceanLabelK {
+    const float* elev; int* label;
+    PB_DEV void operator()(int r) const { label[r] = elev[r] <= 0 ? 1 : 0; }
+};
+struct RootToPlateK {
+    const int* parent; int* r_plate;
+    PB_DEV void operator()(int r) const { r_plate[r] = uf_find(parent, r); }
+};
+struct ClassifyImportedK {
+    Csr g; const float* elev; uint8_t* mountain; uint8_t* coastline; uint8_t* ocean;
+    PB_DEV void operator()(int r) const {
+        const float e = elev[r];
+        ocean[r] = e <= 0 ? 1 : 0;
+        mountain[r] = (e > 0 && (double)e > 0.5) ? 1 : 0;
+        uint8_t coast = 0;
+        if (e > 0) for (int i = g.off[r], end = g.off[r + 1]; i < end; i++) if (elev[g.adj[i]] <= 0) { coast = 1; break; }
+        coastline[r] = coast;
+    }
+};
+
 struct PlateTableIn {    // parallel arrays in plateSeeds order
     int n = 0;
     const int* ids = nullptr; const uint8_t* isOcean = nullptr; const double* pole = nullptr; const double* omega = nullptr;
@@ -221,7 +263,7 @@ struct Plates {
     Mesh* m;
     DevBuf<int> cOff, cAdj, cPlate, parent, size, scratch, pidx, area, first, toSuper, seedsDev, oldPlate;
     DevBuf<float> cXyz;
-    DevBuf<uint8_t> simplexTab, isSeed, inMain;
+    DevBuf<uint8_t> simplexTab, isSeed, inMain, image;
     DevBuf<unsigned long long> word, best;
     explicit Plates(Mesh* mesh) : m(mesh) {}
 
@@ -332,6 +374,28 @@ struct Plates {
         }
         dev_copy(r_plate, hPlate.data(), sizeof(int) * (size_t)N, 0, s);
         stream_sync(s);
+    }
+
+    // importHeightmap: sampleHeightmap (:715-727).  pixels: host u8[W*H]; elev: device float[N]
+    void sample_heightmap(const uint8_t* pixels, int W, int H, float* elev) {
+        if (W < 1 || H < 1) throw Error("image is empty");
+        const Exec& x = m->ex();
+        dev_copy(image.ensure((size_t)W * H), pixels, (size_t)W * H, 0, x.stream);
+        x.for_each(m->N, SampleHeightmapK{m->xyz.p, image.p, W, H, elev});
+        stream_sync(x.stream);
+    }
+    // deriveSyntheticPlates (:733-769): r_plate[r] = lowest id of r's land mass / ocean basin
+    void derive_synthetic_plates(const float* elev, int* r_plate) {
+        const Exec& x = m->ex();
+        const int N = m->N;
+        parent.ensure(N); size.ensure(N); oldPlate.ensure(N);
+        x.for_each(N, LandOceanLabelK{elev, oldPlate.p});
+        x.for_each(N, PlateCcInitK{parent.p, size.p});
+        x.for_each(N, PlateCcHookK{m->csr(), oldPlate.p, parent.p});
+        x.for_each(N, RootToPlateK{parent.p, r_plate});
+    }
+    void classify_imported(const float* elev, uint8_t* mountain, uint8_t* coastline, uint8_t* ocean) {
+        m->ex().for_each(m->N, ClassifyImportedK{m->csr(), elev, mountain, coastline, ocean});
     }
 
     // r_plate: device int[N]; r_super: device int[N] (out)

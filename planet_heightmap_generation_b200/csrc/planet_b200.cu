@@ -48,6 +48,7 @@ struct pb_mesh {
     std::unique_ptr<pb::Plates> plates;
     pb::MeshTriangles triangles;
     pb::DevBuf<float> sTriOut;
+    pb::DevBuf<uint8_t> sMaskA, sMaskB, sMaskC;
     pb::DevBuf<int> sPlateIO, sSuperIO;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
@@ -460,6 +461,41 @@ pb_status pb_build_super_plates(pb_mesh* mesh, const int32_t* r_plate, const pb_
             superOut->omega[sp] = o.omega[sp]; superOut->isOcean[sp] = o.isOcean[sp]; superOut->density[sp] = o.density[sp];
         }
         m.arg_back(r_superPlate, dSuper, (size_t)m.N);
+        m.finish();
+    });
+}
+
+// ---- importHeightmap pieces ---------------------------------------------------------------------------------------------
+pb_status pb_sample_heightmap(pb_mesh* mesh, const uint8_t* grayscale, int32_t width, int32_t height, float* r_elevation) {
+    return guard([&] {
+        need(mesh && grayscale && r_elevation, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        float* d = m.arg_out(r_elevation, (size_t)m.N, m.sElev);
+        plates_of(mesh).sample_heightmap(grayscale, width, height, d);
+        m.arg_back(r_elevation, d, (size_t)m.N);
+        m.finish();
+    });
+}
+pb_status pb_derive_synthetic_plates(pb_mesh* mesh, const float* r_elevation, int32_t* r_plate) {
+    return guard([&] {
+        need(mesh && r_elevation && r_plate, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        const float* e = m.arg_in(r_elevation, (size_t)m.N, m.sElev);
+        int* d = m.arg_out(r_plate, (size_t)m.N, mesh->sPlateIO);
+        plates_of(mesh).derive_synthetic_plates(e, d);
+        m.arg_back(r_plate, d, (size_t)m.N);
+        m.finish();
+    });
+}
+pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, uint8_t* mountain_r, uint8_t* coastline_r, uint8_t* ocean_r) {
+    return guard([&] {
+        need(mesh && r_elevation && mountain_r && coastline_r && ocean_r, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        const size_t N = (size_t)m.N;
+        const float* e = m.arg_in(r_elevation, N, m.sElev);
+        uint8_t* a = m.arg_out(mountain_r, N, mesh->sMaskA); uint8_t* b = m.arg_out(coastline_r, N, mesh->sMaskB); uint8_t* c = m.arg_out(ocean_r, N, mesh->sMaskC);
+        plates_of(mesh).classify_imported(e, a, b, c);
+        m.arg_back(mountain_r, a, N); m.arg_back(coastline_r, b, N); m.arg_back(ocean_r, c, N);
         m.finish();
     });
 }

@@ -1,11 +1,11 @@
 """Host mirror of the reference's Web Worker command layer (js/planet-worker.js:136-677, 944-954).
 
 `PlanetWorker.onmessage(data)` takes the same message objects the main thread posts (`cmd`: generate | reapply |
-editRecompute | computeClimate, same field names) and returns the reply the worker would post (`type`: done |
+editRecompute | computeClimate | importHeightmap, same field names) and returns the reply the worker would post (`type`: done |
 reapplyDone | editDone | climateDone | error, same keys), with typed arrays as numpy arrays and JS Sets posted as lists.
-Every stage runs through the C ABI on the GPU; the retained state `W` (:277-292) is one DeviceMesh (mesh, r_xyz,
-neighborDist and the climate fields stay in HBM) plus the small host-side plate tables.  `importHeightmap` is not
-built (image sampling is outside the path).
+`importHeightmap` (:771-942) is handled too.  Every stage runs through the C ABI on the GPU; the retained state `W`
+(:277-292) is one DeviceMesh (mesh, r_xyz, neighborDist and the climate fields stay in HBM) plus the small host-side
+plate tables.
 
 Differences from the reference, by construction:
   * `seed` must be given (the reference draws `Math.random()` when it is missing, :145);
@@ -47,11 +47,11 @@ class PlanetWorker:
     # ---- dispatch (js/planet-worker.js:944-954) ----------------------------------------------------------------------
     def onmessage(self, data: dict) -> dict:
         handlers = {"generate": self._generate, "reapply": self._reapply, "editRecompute": self._edit_recompute,
-                    "computeClimate": self._compute_climate}
+                    "computeClimate": self._compute_climate, "importHeightmap": self._import_heightmap}
         cmd = data.get("cmd")
         if cmd not in handlers:
             return {"type": "error", "message": f"Unknown command: {cmd}"}
-        if cmd != "generate" and self.W is None:
+        if cmd not in ("generate", "importHeightmap") and self.W is None:
             return {"type": "error", "message": f"No retained state for {cmd}"}
         try:
             return handlers[cmd](data)
@@ -208,6 +208,78 @@ class PlanetWorker:
                                                        "hydraulicErosion", "thermalErosion", "ridgeSharpening", "glacialErosion",
                                                        "continentSizeVariety", "temperatureOffset", "precipitationOffset",
                                                        "landCoverage")} | {"seed": seed})
+        return reply
+
+    # ---- importHeightmap (:771-942) ------------------------------------------------------------------------------------------
+    def _import_heightmap(self, data):
+        import ctypes as C
+        N, jitter = int(data["N"]), float(data["jitter"])
+        if data.get("seed") is None:
+            raise ValueError("importHeightmap needs a seed (the reference would draw Math.random())")
+        seed, skip = data["seed"], bool(data.get("skipClimate"))
+        gray = np.ascontiguousarray(data["grayscale"], np.uint8).reshape(-1)
+        width, height = int(data["imageWidth"]), int(data["imageHeight"])
+        if gray.size != width * height:
+            raise ValueError("grayscale does not hold imageWidth * imageHeight pixels")
+        self.close()
+        temperatureOffset = data.get("temperatureOffset", 0) or 0
+        precipitationOffset = data.get("precipitationOffset", 0) or 0
+        landCoverage = data.get("landCoverage", 0.3) if data.get("landCoverage") is not None else 0.3
+        timing = []
+
+        def stage(name, t0):
+            timing.append({"stage": name, "ms": 1e3 * (time.perf_counter() - t0)})
+
+        t0 = time.perf_counter()
+        mesh = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
+        stage("Sphere mesh", t0); t0 = time.perf_counter()
+        neighborDist = mesh.computeNeighborDist()
+        stage("Neighbor distances", t0); t0 = time.perf_counter()
+        t_xyz = mesh.generateTriangleCenters()
+        triangles, halfedges = mesh.trianglesAndHalfedges()
+        stage("Triangle centers", t0); t0 = time.perf_counter()
+        n, dll = mesh.numRegions, mesh.lib.dll
+        r_elevation = np.empty(n, np.float32)
+        mesh._begin(r_elevation)
+        mesh.lib.check(dll.pb_sample_heightmap(mesh._mesh, gray.ctypes.data, width, height, r_elevation.ctypes.data))
+        stage("Sample heightmap", t0); t0 = time.perf_counter()
+        prePostElev = r_elevation.copy()
+        post = runPostProcessing(mesh, mesh.r_xyz, r_elevation, {k: data.get(k, 0) or 0 for k in _SLIDERS}, neighborDist, seed)
+        stage("Terrain post-processing", t0); t0 = time.perf_counter()
+        r_plate = np.empty(n, np.int32)
+        mesh.lib.check(dll.pb_derive_synthetic_plates(mesh._mesh, r_elevation.ctypes.data, r_plate.ctypes.data))
+        plateSeeds = [int(r) for r in np.nonzero(r_plate == np.arange(n))[0]]
+        plateIsOcean = {s for s in plateSeeds if r_elevation[s] <= 0}
+        plateVec = {s: [0, 0, 0] for s in plateSeeds}
+        stage("Synthetic plates", t0)
+        masks = [np.empty(n, np.uint8) for _ in range(3)]
+        mesh.lib.check(dll.pb_classify_imported_regions(mesh._mesh, r_elevation.ctypes.data, *(m.ctypes.data for m in masks)))
+        debugLayers = {"erosionDelta": post["dl_erosionDelta"]}
+        wind = ocean = precip = temp = None
+        if not skip:
+            t0 = time.perf_counter()
+            wind, ocean, precip, temp, _, _ = self._climate(mesh, r_elevation, plateIsOcean, r_plate, seed, temperatureOffset,
+                                                            precipitationOffset, landCoverage, debugLayers)
+            stage("Climate (wind, ocean currents, precipitation, temperature, Köppen)", t0)
+        t0 = time.perf_counter()
+        t_elevation = mesh.computeTriangleElevations(r_elevation)
+        stage("Triangle elevations", t0)
+        r_stress = np.zeros(n, np.float32)
+        self.W = dict(mesh=mesh, neighborDist=neighborDist, r_plate=r_plate.copy(), plateSeeds=list(plateSeeds), plateVec=plateVec,
+                      plateIsOcean=set(plateIsOcean), originalPlateIsOcean=set(plateIsOcean), plateDensity={}, plateDensityLand={},
+                      plateDensityOcean={}, prePostElev=prePostElev.copy(), r_elevation_final=r_elevation.copy(), seed=seed, nMag=0,
+                      cachedWind=wind, cachedOcean=ocean)
+        reply = {"type": "done", "triangles": triangles, "halfedges": halfedges, "numRegions": n, "r_xyz": mesh.r_xyz, "t_xyz": t_xyz,
+                 "r_plate": r_plate, "plateSeeds": list(plateSeeds), "plateVec": plateVec,
+                 "plateIsOcean": [s for s in plateSeeds if s in plateIsOcean], "originalPlateIsOcean": [s for s in plateSeeds if s in plateIsOcean],
+                 "plateDensity": {}, "plateDensityLand": {}, "plateDensityOcean": {}, "prePostElev": prePostElev,
+                 "r_elevation": r_elevation, "t_elevation": t_elevation, "mountain_r": _mask_to_list(masks[0]),
+                 "coastline_r": _mask_to_list(masks[1]), "ocean_r": _mask_to_list(masks[2]), "r_stress": r_stress}
+        reply.update(self._climate_fields(wind, ocean, precip, temp))
+        reply.update(skipClimate=skip, seed=seed, nMag=0, debugLayers=debugLayers, _timing=[], _pipelineTiming=timing,
+                     _postTiming=post.get("postTiming", []), _workerTotal=sum(s["ms"] for s in timing),
+                     _params={"N": N, "P": 0, "jitter": jitter, "nMag": 0, "numContinents": 0, "seed": seed,
+                              **{k: data.get(k) for k in _SLIDERS}})
         return reply
 
     # ---- reapply (:341-440) ----------------------------------------------------------------------------------------------

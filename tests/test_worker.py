@@ -143,3 +143,42 @@ def test_worker_commands_match_the_reference_handlers(backend, oracle):
     assert same(r["prePostElev"], ow.pre) and same(r["r_elevation"], elev) and same(r["debugLayers"]["erosionDelta"], delta)
     assert same(r["debugLayers"]["koppen"], koppen) and same(r["r_stress"], ow.oe.get("r_stress"))
     w.close()
+
+
+def test_import_heightmap_command(backend, oracle):
+    """importHeightmap (:771-942): bilinear sampling of an equirectangular grayscale image, post-processing, synthetic plates
+    from the land / ocean components, region classes, climate — against the oracle's restatement of the same handler."""
+    from oracle.mesh_hull import build_sphere_from_points
+    rng = np.random.default_rng(3)
+    W_, H_ = 96, 48
+    yy, xx = np.mgrid[0:H_, 0:W_]
+    img = 110 + 90 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 40 * rng.random((H_, W_))
+    img[(np.sin(xx / 5.0 + yy / 11.0) > 0.2)] = 0            # oceans: black
+    gray = np.clip(np.round(img), 0, 255).astype(np.uint8)
+    msg = dict(cmd="importHeightmap", N=3000, jitter=0.75, grayscale=gray.reshape(-1), imageWidth=W_, imageHeight=H_, smoothing=0.1,
+               glacialErosion=0.5, hydraulicErosion=0.5, thermalErosion=0.1, ridgeSharpening=0.5, terrainWarp=0.75, seed=77)
+    w = PlanetWorker(lib=backend)
+    r = w.onmessage(msg)
+    assert r["type"] == "done", r
+    mesh, xyz = build_sphere_from_points(oracle.fibonacci_sphere(3000, 0.75, 77))
+    nd = oracle.neighbor_dist(mesh, xyz)
+    elev = oracle.sample_heightmap(mesh, xyz, gray.reshape(-1), W_, H_)
+    assert same(r["prePostElev"], elev) and (elev == np.float32(-0.5)).any() and (elev > 0).any()
+    delta, _ = oracle.run_post_processing(mesh, xyz, elev, {k: msg[k] for k in SLIDER_KEYS}, nd, 77, None)
+    assert same(r["r_elevation"], elev) and same(r["debugLayers"]["erosionDelta"], delta)
+    r_plate, seeds, pio = oracle.derive_synthetic_plates(mesh, elev)
+    assert same(r["r_plate"], r_plate) and r["plateSeeds"] == seeds and set(r["plateIsOcean"]) == pio and len(seeds) >= 2
+    m, c, o = oracle.classify_imported(mesh, elev)
+    assert r["mountain_r"] == [int(i) for i in np.nonzero(m)[0]] and r["coastline_r"] == [int(i) for i in np.nonzero(c)[0]]
+    assert r["ocean_r"] == [int(i) for i in np.nonzero(o)[0]] and not r["r_stress"].any()
+    clim = oracle.Climate(mesh, xyz)
+    koppen = clim.run_all(elev, pio, r_plate, 77)
+    assert same(r["debugLayers"]["koppen"], koppen) and same(r["r_precip_summer"], clim.get("r_precip_summer"))
+    # the imported planet is retained: reapply works on it (:341)
+    r2 = w.onmessage(dict(cmd="reapply", smoothing=0.0, glacialErosion=0.0, hydraulicErosion=0.3, thermalErosion=0.0, ridgeSharpening=0.0,
+                          terrainWarp=0.0, skipClimate=True))
+    elev2 = oracle.sample_heightmap(mesh, xyz, gray.reshape(-1), W_, H_)
+    oracle.run_post_processing(mesh, xyz, elev2, dict(smoothing=0.0, glacialErosion=0.0, hydraulicErosion=0.3, thermalErosion=0.0,
+                                                      ridgeSharpening=0.0, terrainWarp=0.0), nd, 77, None)
+    assert r2["type"] == "reapplyDone" and same(r2["r_elevation"], elev2)
+    w.close()
