@@ -280,6 +280,17 @@ pb_status pb_derive_synthetic_plates(pb_mesh* mesh, const float* r_elevation, in
 pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, uint8_t* mountain_r, uint8_t* coastline_r,
                                        uint8_t* ocean_r);
 
+/* ---- per-region colour ramps -------------------------------------------------------------------
+ * pb_region_colors fills rgb[3*numRegions] (Float32 colour buffer order r,g,b) for one of the renderer's colour modes:
+ *   PB_COLOR_TERRAIN         elevationToColor(r_elevation[r])                     js/color-map.js:116-125
+ *   PB_COLOR_BIOME           smoothBiomeColors(mesh, koppen, r_elevation)         js/planet-mesh.js:30-62 (biomeColor, js/color-map.js:73-114)
+ *   PB_COLOR_HEIGHTMAP / PB_COLOR_LAND_HEIGHTMAP / PB_COLOR_LAND_MASK             js/planet-mesh.js:64-80
+ *   PB_COLOR_BIOME_RAW       biomeColor(koppen[r], r_elevation[r]) without the neighbour blend
+ * r_koppen is only read by the two biome modes.  Arrays follow the context's pointer mode. */
+enum { PB_COLOR_TERRAIN = 0, PB_COLOR_BIOME = 1, PB_COLOR_HEIGHTMAP = 2, PB_COLOR_LAND_HEIGHTMAP = 3, PB_COLOR_LAND_MASK = 4,
+       PB_COLOR_BIOME_RAW = 5 };
+pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation, const uint8_t* r_koppen, float* rgb);
+
 /* ---- triangles: what the worker's `done` / `reapplyDone` / `editDone` replies carry for the renderer ----------------
  * pb_mesh_get_triangles: SphereMesh.triangles / .halfedges (js/sphere-mesh.js:94-100) of the mesh, 3*numTriangles ints
  * each, in the canonical numbering (csrc/pb_meshgen.h); numTriangles = 2*numRegions - 4.

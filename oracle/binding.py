@@ -399,3 +399,15 @@ def classify_imported(mesh, elev):
     lib().orc_classify_imported(*_mesh_args(mesh), _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(m, C.c_uint8), _p(c, C.c_uint8),
                                 _p(o, C.c_uint8))
     return m, c, o
+
+
+# ---- colour ramps (js/color-map.js, js/planet-mesh.js:30-80) --------------------------------------------------------------
+COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5}
+
+
+def region_colors(mesh, mode, elev, koppen=None):
+    out = np.empty(3 * mesh.numRegions, np.float32)
+    k = np.zeros(mesh.numRegions, np.uint8) if koppen is None else np.ascontiguousarray(koppen, np.uint8)
+    lib().orc_region_colors(*_mesh_args(mesh), C.c_int(COLOR_MODES[mode]), _p(np.ascontiguousarray(elev, np.float32), C.c_float),
+                            _p(k, C.c_uint8), _p(out, C.c_float))
+    return out

@@ -73,6 +73,7 @@ SYMBOLS = {
     "pb_sample_heightmap": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "pb_derive_synthetic_plates": (C.c_int, [_vp, _vp, _vp]),
     "pb_classify_imported_regions": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pb_region_colors": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "pb_mesh_num_triangles": (_i32, [_vp]),
     "pb_mesh_get_triangles": (C.c_int, [_vp, _vp, _vp]),
     "pb_generate_triangle_centers": (C.c_int, [_vp, _vp]),

@@ -8,6 +8,8 @@
 #include "pb_meshgen.h"
 #include "pb_plates.h"
 #include "pb_coarse.h"
+#include "pb_climate.h"
+#include "pb_colors.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -49,6 +51,7 @@ struct pb_mesh {
     pb::MeshTriangles triangles;
     pb::DevBuf<float> sTriOut;
     pb::DevBuf<uint8_t> sMaskA, sMaskB, sMaskC;
+    pb::DevBuf<float> sColorRaw;
     pb::DevBuf<int> sPlateIO, sSuperIO;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
@@ -496,6 +499,30 @@ pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, 
         uint8_t* a = m.arg_out(mountain_r, N, mesh->sMaskA); uint8_t* b = m.arg_out(coastline_r, N, mesh->sMaskB); uint8_t* c = m.arg_out(ocean_r, N, mesh->sMaskC);
         plates_of(mesh).classify_imported(e, a, b, c);
         m.arg_back(mountain_r, a, N); m.arg_back(coastline_r, b, N); m.arg_back(ocean_r, c, N);
+        m.finish();
+    });
+}
+
+// ---- colour ramps ---------------------------------------------------------------------------------------------------------
+pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation, const uint8_t* r_koppen, float* rgb) {
+    return guard([&] {
+        need(mesh && r_elevation && rgb, "NULL argument");
+        need(mode >= 0 && mode <= 5, "unknown colour mode");
+        const bool biome = mode == pb::COLOR_BIOME || mode == pb::COLOR_BIOME_RAW;
+        need(!biome || r_koppen, "biome colours need r_koppen");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        const size_t N = (size_t)m.N;
+        const float* e = m.arg_in(r_elevation, N, m.sElev);
+        const uint8_t* k = biome ? m.arg_in(r_koppen, N, mesh->sMaskA) : nullptr;
+        float* out = m.arg_out(rgb, 3 * N, mesh->sTriOut);
+        if (mode == pb::COLOR_BIOME) {
+            float* raw = mesh->sColorRaw.ensure(3 * N);
+            m.ex().for_each(m.N, pb::RegionColorK{mode, e, k, raw});
+            m.ex().for_each(m.N, pb::BiomeBlendK{m.csr(), raw, out});
+        } else {
+            m.ex().for_each(m.N, pb::RegionColorK{mode, e, k, out});
+        }
+        m.arg_back(rgb, out, 3 * N);
         m.finish();
     });
 }

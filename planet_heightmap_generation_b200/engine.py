@@ -206,6 +206,20 @@ class DeviceMesh:
             self._mesh, self._ptr(r_elevation, "f32", self.numRegions, "r_elevation"), self._ptr(out, "f32", self.numTriangles, "t_elevation")))
         return out
 
+    COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5}
+
+    def regionColors(self, mode: str, r_elevation, r_koppen=None, out=None):
+        """Per-region r,g,b (Float32, 3·numRegions) of one of the renderer's colour modes: elevationToColor, smoothBiomeColors /
+        biomeColor, heightmapColor, landHeightmapColor, landMaskColor (js/color-map.js:73-125, js/planet-mesh.js:30-80)."""
+        n = self.numRegions
+        if out is None:
+            out = self._new(r_elevation, "f32", 3 * n)
+        self._begin(r_elevation, r_koppen, out)
+        self.lib.check(self.lib.dll.pb_region_colors(
+            self._mesh, self.COLOR_MODES[mode], self._ptr(r_elevation, "f32", n, "r_elevation"),
+            None if r_koppen is None else self._ptr(r_koppen, "u8", n, "r_koppen"), self._ptr(out, "f32", 3 * n, "rgb")))
+        return out
+
     def generateFibonacciSphere(self, N: int, jitter: float, seed: float, out=None):
         """generateFibonacciSphere + the pole vertex (js/sphere-mesh.js:9-37, 179-183): 3·(N+1) floats."""
         if out is None:
