@@ -186,6 +186,25 @@ struct Elevation {
         run_collisions(0, tP, r_plate_dev, NZ(0), small);
         const bool dual = SP != nullptr;
         if (dual) { const PlateTab tS = dSP.upload(*SP, x.stream); run_collisions(1, tS, r_super_dev, NZ(0), super); }
+
+        // 5a. the two coast-distance fills (:411, 426) read only r_plate and the ocean flags of the plates: their seed lists are
+        // built while the collision kernels run, and the fills — the longest serial chains of the call — start before anything else
+        struct Joiner { std::thread* t; int n; ~Joiner() { for (int k = 0; k < n; k++) if (t[k].joinable()) t[k].join(); } };
+        std::vector<uint8_t> isOcean(N);
+        for (int r = 0; r < N; r++) isOcean[r] = P.ocean(r_plate[r]) ? 1 : 0;
+        OrderedCells coastSeeds; coastSeeds.reset(N);
+        std::vector<int> landCoastSeeds;
+        for (int r = 0; r < N; r++) {
+            if (isOcean[r]) continue;
+            for (int j = off[r], e = off[r + 1]; j < e; j++) if (isOcean[adj[j]]) { coastSeeds.add(adj[j]); landCoastSeeds.push_back(r); break; }
+        }
+        std::vector<float> hd[5];
+        std::thread fill[5];
+        fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
+        fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
+        Joiner joinFills{fill, 5};
+        lap("ocean mask + coast seeds");
+
         stream_sync(x.stream);
         lap("collisions (device) + d2h");
 
@@ -201,7 +220,7 @@ struct Elevation {
         std::thread prop[2];
         prop[0] = std::thread([&] { propagate_stress(off, adj, N, sSt, sSu, r_plate, P, decayFactor, subductDecayFactor, numPasses); });
         if (dual) prop[1] = std::thread([&] { propagate_stress(off, adj, N, pSt, pSu, r_super, *SP, decayFactor, subductDecayFactor, numPasses); });
-        struct Joiner { std::thread* t; int n; ~Joiner() { for (int k = 0; k < n; k++) if (t[k].joinable()) t[k].join(); } } joinProp{prop, 2};
+        Joiner joinProp{prop, 2};
 
         // 2. blend (:250-327)
         OrderedCells mountain, coastline, ocean;
@@ -253,23 +272,9 @@ struct Elevation {
                 if (k >= 0 && plateRep[k] >= 0) (P.ocean(pid) ? ocean : coastline).add(plateRep[k]);
             }
         }
-        std::vector<uint8_t> isOcean(N);
-        for (int r = 0; r < N; r++) isOcean[r] = P.ocean(r_plate[r]) ? 1 : 0;
-        OrderedCells coastSeeds; coastSeeds.reset(N);
-        std::vector<int> landCoastSeeds;
-        for (int r = 0; r < N; r++) {
-            if (isOcean[r]) continue;
-            for (int j = off[r], e = off[r + 1]; j < e; j++) if (isOcean[adj[j]]) { coastSeeds.add(adj[j]); landCoastSeeds.push_back(r); break; }
-        }
-        lap("representatives + seeds");
-        // 5a. three of the five randomized fills (:393, 411, 426) read only the sets and the ocean mask: they start now and
-        // overlap the rest of the propagation; the two that need the propagated subduction factor follow below
-        std::vector<float> hd[5];
-        std::thread fill[5];
+        lap("representatives");
+        // 5b. the ocean-distance fill (:393) needs the finished sets but not the propagation: it overlaps the rest of it
         fill[1] = std::thread([&] { distance_field(off, adj, N, ocean.items, coastline.in.data(), seed + 2, hd[1]); });
-        fill[3] = std::thread([&] { distance_field(off, adj, N, coastSeeds.items, nullptr, seed + 4, hd[3]); });
-        fill[4] = std::thread([&] { distance_field(off, adj, N, landCoastSeeds, isOcean.data(), seed + 5, hd[4]); });
-        Joiner joinFills{fill, 5};
         // 3. join the propagation, blend its results (:343-361)
         prop[0].join();
         if (dual) prop[1].join();
@@ -288,7 +293,7 @@ struct Elevation {
         for (int r : mountain.items) if ((double)sub[r] < 0.55) { stressMountain.push_back(r); stop[r] = 1; }
         for (int r : coastline.items) stop[r] = 1;
         for (int r : ocean.items) stop[r] = 1;
-        // 5b. the two fills that depend on the propagation (:392, 394); all five run concurrently with the capped BFS below
+        // 5c. the two fills that depend on the propagation (:392, 394); all five run concurrently with the capped BFS below
         fill[0] = std::thread([&] { distance_field(off, adj, N, stressMountain, ocean.in.data(), seed + 1, hd[0]); });
         fill[2] = std::thread([&] { distance_field(off, adj, N, coastline.items, stop.data(), seed + 3, hd[2]); });
 
