@@ -3,24 +3,22 @@
 // One process per GPU.  Every rank owns a contiguous cell-id range plus the halo cells its rows read; the two
 // ping-pong field buffers and two small flag arrays of a shard are ordinary cudaMalloc memory exported with CUDA
 // IPC, so a peer's kernels store straight into them over NVLink / NVSwitch — no NCCL call and no host round trip
-// per sweep.  Pass k of a rank is
-//     wait   until every peer's flag says "my pass k-1 values are in your halo"      (k_wait_flags, one thread)
-//     sweep  owned rows: buf[k%2] = smoothField(buf[(k-1)%2])                       (SmoothFieldK, owned rows only)
-//     push   my boundary cells of buf[k%2] into each peer's buf[k%2] halo slice      (k_halo_push, peer stores)
-//     flag   __threadfence_system(); peer.flags[me] = epoch + k                      (k_flag_set)
-// The four steps are ONE kernel launch per pass (k_shard_sweep): thread 0 of every CTA spins on the flags before
-// the CTA reads anything, and the last CTA to finish (ticket counter) pushes the boundary and raises the flags.
-// A peer cannot overwrite a halo slot that is still being read: its pass k push follows its pass k sweep, which
-// waited for this rank's pass k-1 flag, i.e. for this rank to have finished reading that buffer in pass k-1.
+// per sweep.  Pass k of a rank is ONE kernel launch (k_shard_sweep):
+//     the first few CTAs   wait until every peer's flag says "my pass k-1 values are in your halo", compute the rows on
+//                          the send lists (exactly the rows that read halo slots), store each new value straight into
+//                          the peer's halo slot, fence system-wide, and the last of them (ticket) writes
+//                          peer.flags[me] = epoch + k;
+//     all other CTAs       sweep the remaining owned rows, buf[k%2] = smoothField(buf[(k-1)%2]), without waiting.
+// A peer cannot overwrite a halo slot that is still being read: its pass k stores follow its own wait for this rank's
+// pass k-1 flag, which is raised only after this rank's boundary rows — the only readers of halo slots — are done.
+// k_wait_flags / k_flag_set (one thread each) bracket a call: the previous call of every peer must be over before
+// halo slots are reused, and the final halo values must have arrived before the result is copied out.
 #pragma once
 #include "pb_engine.h"
 
 #if PB_CUDA
 namespace pb {
 
-__global__ void k_halo_push(const float* __restrict__ src, const int* __restrict__ idx, int n, float* __restrict__ peerDst) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) peerDst[i] = src[idx[i]];
-}
 __global__ void k_flag_set(volatile int* peerFlag, int value) {
     __threadfence_system();
     *peerFlag = value;
