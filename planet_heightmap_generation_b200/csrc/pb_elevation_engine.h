@@ -92,10 +92,18 @@ struct Elevation {
         dev_copy(out.setCode.data(), o.setCode, (size_t)N, 1, x.stream);
     }
 
+#if defined(__GNUC__)
+#define PB_PREFETCH(p) __builtin_prefetch((p), 0, 1)
+#else
+#define PB_PREFETCH(p) ((void)0)
+#endif
     // ---- host-serial pieces ------------------------------------------------------------------------------------
     static void propagate_stress(const int* off, const int* adj, int N, std::vector<float>& stress, std::vector<float>& sub,
                                  const int* plate, const PlateTableHost& P, double decay, double subDecay, int numPasses) {   // :127-159
+        const bool dbgT = getenv("PB_DEBUG") != nullptr;
+        const auto tStart = std::chrono::steady_clock::now();
         std::vector<int> frontier, next;
+        size_t visits = 0;
         for (int r = 0; r < N; r++) if (stress[r] > 0.01f && (double)stress[r] > 0.01) frontier.push_back(r);
         for (int pass = 0; pass < numPasses && !frontier.empty(); pass++) {
             next.clear();
@@ -108,17 +116,18 @@ struct Elevation {
                 if (propagated < 0.005) continue;
                 for (int j = off[r], e = off[r + 1]; j < e; j++) {
                     const int nb = adj[j];
-                    if (plate[nb] == pl && propagated > (double)stress[nb]) { stress[nb] = (float)propagated; sub[nb] = sf; next.push_back(nb); }
+                    if (plate[nb] == pl && propagated > (double)stress[nb]) {
+                        stress[nb] = (float)propagated; sub[nb] = sf; next.push_back(nb);
+                        PB_PREFETCH(adj + off[nb]);          // read in the next pass
+                    }
                 }
             }
+            visits += frontier.size();
             frontier.swap(next);
         }
+        if (dbgT) fprintf(stderr, "[pb] propagate_stress: %zu frontier visits, %.2f ms\n", visits,
+                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count());
     }
-#if defined(__GNUC__)
-#define PB_PREFETCH(p) __builtin_prefetch((p), 0, 1)
-#else
-#define PB_PREFETCH(p) ((void)0)
-#endif
     struct ParkMillerInt {   // makeRandInt (js/rng.js:8-11); the state is an integer < 2^31, so the JS double
         unsigned long long s;  // arithmetic (s*16807) % 2147483647 is reproduced exactly in 64-bit integers
         explicit ParkMillerInt(double seed) { s = (unsigned long long)(fmod(fabs(floor(seed * 9301.0 + 49297.0)), 2147483646.0) + 1.0); }
