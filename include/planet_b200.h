@@ -299,6 +299,9 @@ pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation
  * Arrays follow the context's pointer mode. */
 int32_t pb_mesh_num_triangles(const pb_mesh* mesh);
 pb_status pb_mesh_get_triangles(pb_mesh* mesh, int32_t* triangles, int32_t* halfedges);
+/* SphereMesh._adjTriList (js/sphere-mesh.js:128-143, read by r_circulate_t): for every adjacency slot the triangle on the
+ * inner side of that half-edge; numEdges ints. */
+pb_status pb_mesh_get_adj_triangles(pb_mesh* mesh, int32_t* adjTriList);
 pb_status pb_generate_triangle_centers(pb_mesh* mesh, float* t_xyz);
 pb_status pb_compute_triangle_elevations(pb_mesh* mesh, const float* r_elevation, float* t_elevation);
 

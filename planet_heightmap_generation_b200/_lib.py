@@ -76,6 +76,7 @@ SYMBOLS = {
     "pb_region_colors": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "pb_mesh_num_triangles": (_i32, [_vp]),
     "pb_mesh_get_triangles": (C.c_int, [_vp, _vp, _vp]),
+    "pb_mesh_get_adj_triangles": (C.c_int, [_vp, _vp]),
     "pb_generate_triangle_centers": (C.c_int, [_vp, _vp]),
     "pb_compute_triangle_elevations": (C.c_int, [_vp, _vp, _vp]),
     "pb_generate_fibonacci_sphere": (C.c_int, [_vp, _i32, C.c_double, C.c_double, _vp]),

@@ -435,6 +435,23 @@ struct HalfedgeK {
         half[side] = 3 * found + pos;
     }
 };
+// _adjTriList (js/sphere-mesh.js:128-143): for the k-th neighbour b of region a, the triangle that holds side a→b, i.e.
+// (a, b, c) counter-clockwise with c = the entry before b in a's clockwise row
+struct AdjTriK {
+    Csr g; const int* start; const int* tri; int* adjTri; int* bad;
+    PB_DEV void operator()(int a) const {
+        const int s = g.off[a], d = g.off[a + 1] - s;
+        for (int k = 0; k < d; k++) {
+            const int b = g.adj[s + k], c = g.adj[s + (k == 0 ? d - 1 : k - 1)];
+            int v0 = a, v1 = b, v2 = c;
+            if (b < a && b < c) { v0 = b; v1 = c; v2 = a; } else if (c < a && c < b) { v0 = c; v1 = a; v2 = b; }
+            int found = -1;
+            for (int u = start[v0]; u < start[v0 + 1]; u++) if (tri[3 * u + 1] == v1 && tri[3 * u + 2] == v2) { found = u; break; }
+            if (found < 0) atomic_add(bad, 1);
+            adjTri[s + k] = found;
+        }
+    }
+};
 // generateTriangleCenters (js/sphere-mesh.js:206-219) and computeTriangleElevations (js/planet-worker.js:29-37)
 struct TriCentersK {
     const int* tri; const float* xyz; float* t_xyz;
@@ -451,7 +468,7 @@ struct TriElevationK {
 };
 
 struct MeshTriangles {
-    DevBuf<int> cnt, start, tri, half, flag;
+    DevBuf<int> cnt, start, tri, half, flag, adjTri;
     DevBuf<uint8_t> scanTemp;
     int T = 0;
     // builds (once per mesh) the device copies; tri / half are 3T ints
@@ -481,6 +498,11 @@ struct MeshTriangles {
         dev_copy(&bad, flag.p, sizeof(int), 1, ex.stream);
         stream_sync(ex.stream);
         if (bad) throw Error("mesh rows are not consistent circulations: " + std::to_string(bad) + " sides without a twin");
+        adjTri.ensure((size_t)3 * total);            // E = 3T directed edges
+        ex.for_each(N, AdjTriK{g, start.p, tri.p, adjTri.p, flag.p + 1});
+        dev_copy(&bad, flag.p + 1, sizeof(int), 1, ex.stream);
+        stream_sync(ex.stream);
+        if (bad) throw Error("mesh rows are not consistent circulations: " + std::to_string(bad) + " edges without an inner triangle");
         T = total;
     }
 };

@@ -541,6 +541,15 @@ pb_status pb_mesh_get_triangles(pb_mesh* mesh, int32_t* triangles, int32_t* half
         m.finish();
     });
 }
+pb_status pb_mesh_get_adj_triangles(pb_mesh* mesh, int32_t* adjTriList) {
+    return guard([&] {
+        need(mesh && adjTriList, "NULL argument");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        mesh->triangles.build(m.ex(), m.csr(), m.N);
+        pb::dev_copy(adjTriList, mesh->triangles.adjTri.p, sizeof(int) * (size_t)m.E, m.hostMode() ? 1 : 2, m.ex().stream);
+        m.finish();
+    });
+}
 pb_status pb_generate_triangle_centers(pb_mesh* mesh, float* t_xyz) {
     return guard([&] {
         need(mesh && t_xyz, "NULL argument");

@@ -189,6 +189,13 @@ class DeviceMesh:
         self.lib.check(self.lib.dll.pb_mesh_get_triangles(self._mesh, t.ctypes.data, h.ctypes.data))
         return t, h
 
+    def adjTriList(self):
+        """SphereMesh._adjTriList (js/sphere-mesh.js:128-143): inner triangle of every adjacency slot (numpy int32[numEdges])."""
+        out = np.empty(self.numEdges, np.int32)
+        self._begin(out)
+        self.lib.check(self.lib.dll.pb_mesh_get_adj_triangles(self._mesh, out.ctypes.data))
+        return out
+
     def generateTriangleCenters(self, out=None):
         """generateTriangleCenters(mesh, r_xyz) (js/sphere-mesh.js:206-219)"""
         if out is None:

@@ -134,6 +134,7 @@ def test_triangles_and_halfedges_match_hull(backend, n, seed):
     tri, half = dm.trianglesAndHalfedges()
     assert dm.numTriangles == mesh.numTriangles
     assert np.array_equal(tri, mesh.triangles) and np.array_equal(half, mesh.halfedges)
+    assert np.array_equal(dm.adjTriList(), mesh.adjTriList)
     # half-edge invariants (js/sphere-mesh.js: s_end_r(s) == s_begin_r(halfedges[s]))
     nxt = np.where(np.arange(tri.size) % 3 == 2, np.arange(tri.size) - 2, np.arange(tri.size) + 1)
     assert np.array_equal(half[half], np.arange(tri.size)) and np.array_equal(tri[nxt], tri[half])
