@@ -646,6 +646,13 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if "hbm_gbs" in peaks else "fallback 6650 GB/s, of fallback"
 
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (1M cells); only
+    # quoted when the bench runs the size the capture was taken at
+    ncu_traffic = {"pb::k_flood_heap": (40.1e6, "profiles/r01_flood_heap_ncu.md (240 310 land cells)"),
+                   "pb::SmoothFieldK": (32.0e6, "profiles/r01_sweeps_ncu.md"),
+                   "pb::ShadowSweepK": (62.0e6, "profiles/r01_sweeps_ncu.md (37.3 MB read + 19-30 MB written)"),
+                   "pb::StarK": (133.2e6, "profiles/r01_mesh_plates_ncu.md")}
+
     def roof(kernel):
         dom = [p for p in prof if p["name"] == kernel]
         if not dom:
@@ -659,6 +666,8 @@ def run_b200(args):
         if ab:
             out["achieved"] = ab / (avg_ms * 1e-3) / 1e9
             out["frac"] = out["achieved"] / peak
+        if d["name"] in ncu_traffic and args.cells == 1_000_000:
+            out["traffic"], out["traffic_source"] = ncu_traffic[d["name"]]
         return out
 
     roofline = roof(dominant)
