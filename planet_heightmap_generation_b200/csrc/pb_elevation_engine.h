@@ -142,6 +142,8 @@ struct Elevation {
     };
     static void distance_field(const int* off, const int* adj, int N, const std::vector<int>& seeds, const uint8_t* isStop, double seed,
                                std::vector<float>& dist) {   // :164-189
+        const bool dbgT = getenv("PB_DEBUG") != nullptr;
+        const auto tStart = std::chrono::steady_clock::now();
         ParkMillerInt randInt(seed);
         dist.assign(N, INFINITY);
         std::vector<int> queue;
@@ -160,6 +162,8 @@ struct Elevation {
                 }
             }
         }
+        if (dbgT) fprintf(stderr, "[pb] distance_field(seed %.0f): %zu seeds, %zu cells, %.2f ms\n", seed, seeds.size(), queue.size(),
+                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count());
     }
 
     // ---- assignElevation ----------------------------------------------------------------------------------------------
