@@ -380,8 +380,9 @@ struct IslandArcK {
     }
 };
 
-// hotspot domes :1239-1372.  The dome list (≤ 35 entries, RNG-placed: class R) is built on the host.
-#define PB_MAX_DOMES 48
+// hotspot domes :1239-1372.  The dome list (RNG-placed: class R) is built on the host: 5 hotspots, each an active dome plus
+// a trail of max(3, 6 + round((u - 0.5)·10)) ≤ 11 domes (:1116-1117, 1153), i.e. at most 60 entries.
+#define PB_MAX_DOMES 64
 struct DomeDev {
     double x, y, z, strength, ux, uy, uz, vx, vy, vz, cosThreshPeak, invS2, swellStrength, cosThreshSwell, invS2Swell,
         driftStretch, calderaDepth, invS2Caldera, ageFactor, riftAngles[3];

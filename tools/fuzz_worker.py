@@ -1,0 +1,53 @@
+"""Randomised end-to-end comparison of the engine (host emulation build of the kernel sources — test infrastructure) with
+the oracle: the worker's generate → reapply → editRecompute → computeClimate sequence on random (N, seed, P, sliders).
+Run on a box without a GPU:  python tools/fuzz_worker.py [rounds] [first_seed]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import binding as oracle  # noqa: E402
+from planet_heightmap_generation_b200._lib import Library  # noqa: E402
+from planet_heightmap_generation_b200.worker import PlanetWorker  # noqa: E402
+from tests.emul.build_emul import build  # noqa: E402
+from tests.test_worker import SLIDER_KEYS, OracleWorker, same  # noqa: E402
+
+
+def main():
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    oracle.build()
+    lib = Library(build())
+    bad = 0
+    for k in range(rounds):
+        rng = np.random.default_rng(first + k)
+        sl = {s: float(np.round(rng.random(), 2)) for s in SLIDER_KEYS}
+        msg = dict(cmd="generate", N=int(rng.integers(1500, 12000)), P=int(rng.choice([5, 8, 12, 20, 40, 80])), jitter=float(rng.choice([0.0, 0.5, 0.75, 1.0])),
+                   nMag=float(np.round(rng.random() * 0.8, 2)), numContinents=int(rng.integers(1, 7)), continentSizeVariety=float(rng.choice([0, 0.5, 1.0])),
+                   temperatureOffset=float(rng.choice([0, -3, 4])), precipitationOffset=float(rng.choice([0, -0.3, 0.3])),
+                   landCoverage=float(rng.choice([0.15, 0.3, 0.5])), seed=int(rng.integers(0, 16777216)), **sl)
+        w, ow = PlanetWorker(lib=lib), OracleWorker(oracle)
+        r = w.onmessage(dict(msg))
+        ok = r["type"] == "done"
+        if ok:
+            elev, delta, koppen = ow.generate(msg)
+            ok = same(r["r_plate"], ow.r_plate) and same(r["prePostElev"], ow.pre) and same(r["r_elevation"], elev) and \
+                same(r["debugLayers"]["koppen"], koppen) and same(r["r_stress"], ow.oe.get("r_stress")) and \
+                all(same(r[f], ow.clim.get(f)) for f in ("r_wind_east_summer", "r_ocean_warmth_winter", "r_precip_summer", "r_temperature_winter"))
+        if ok:
+            sl2 = {s: float(np.round(rng.random(), 2)) for s in SLIDER_KEYS}
+            r2 = w.onmessage(dict(cmd="reapply", **sl2))
+            e2, d2, k2 = ow.reapply(dict(sl2), msg["temperatureOffset"], msg["precipitationOffset"], msg["landCoverage"])
+            ok = r2["type"] == "reapplyDone" and same(r2["r_elevation"], e2) and same(r2["erosionDelta"], d2) and same(r2["windDebugLayers"]["koppen"], k2)
+        print(f"round {k}: N={msg['N']} P={msg['P']} jitter={msg['jitter']} seed={msg['seed']} sliders={sl} -> {'ok' if ok else 'MISMATCH ' + str(r.get('message', ''))}", flush=True)
+        bad += not ok
+        w.close()
+    print("mismatches:", bad)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
