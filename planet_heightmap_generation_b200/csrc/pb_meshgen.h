@@ -369,7 +369,7 @@ struct SphereTriangulator {
         dev_copy(h, fail.p, 2 * sizeof(int), 1, ex.stream);
         dev_copy(&total, dOff + n, sizeof(int), 1, ex.stream);
         stream_sync(ex.stream);
-        if (h[0]) throw Error("spherical Delaunay: " + std::to_string(h[0]) + " region stars could not be closed (duplicate or wildly uneven points?)");
+        if (h[0]) throw Error("spherical Delaunay: " + std::to_string(h[0]) + " region stars could not be closed (duplicate points, a region with more than 32 neighbours, or a point density that varies by orders of magnitude)");
         if (total != 6 * n - 12) throw Error("spherical Delaunay: edge count " + std::to_string(total) + " != 6n-12 (degenerate point set)");
         ex.for_each(n, StarFillK{StarK{n, g, key.p, sid.p, sx.p, sy.p, sz.p, deg.p, rows.p, dOff, dAdj, fail.p}, pos.p});
         ex.for_each(n, MeshGenSymmetryK{n, dOff, dAdj, fail.p + 2});
