@@ -16,6 +16,9 @@ from tests.emul.build_emul import build  # noqa: E402
 from tests.test_worker import SLIDER_KEYS, OracleWorker, same  # noqa: E402
 
 
+NRANGE = (int(os.environ.get("FUZZ_NMIN", 1500)), int(os.environ.get("FUZZ_NMAX", 12000)))
+
+
 def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -25,7 +28,7 @@ def main():
     for k in range(rounds):
         rng = np.random.default_rng(first + k)
         sl = {s: float(np.round(rng.random(), 2)) for s in SLIDER_KEYS}
-        msg = dict(cmd="generate", N=int(rng.integers(1500, 12000)), P=int(rng.choice([5, 8, 12, 20, 40, 80])), jitter=float(rng.choice([0.0, 0.5, 0.75, 1.0])),
+        msg = dict(cmd="generate", N=int(rng.integers(*NRANGE)), P=int(rng.choice([5, 8, 12, 20, 40, 80])), jitter=float(rng.choice([0.0, 0.5, 0.75, 1.0])),
                    nMag=float(np.round(rng.random() * 0.8, 2)), numContinents=int(rng.integers(1, 7)), continentSizeVariety=float(rng.choice([0, 0.5, 1.0])),
                    temperatureOffset=float(rng.choice([0, -3, 4])), precipitationOffset=float(rng.choice([0, -0.3, 0.3])),
                    landCoverage=float(rng.choice([0.15, 0.3, 0.5])), seed=int(rng.integers(0, 16777216)), **sl)
