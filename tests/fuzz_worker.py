@@ -1,6 +1,6 @@
 """Randomised end-to-end comparison of the engine (host emulation build of the kernel sources — test infrastructure) with
 the oracle: the worker's generate → reapply → editRecompute → computeClimate sequence on random (N, seed, P, sliders).
-Run on a box without a GPU:  python tools/fuzz_worker.py [rounds] [first_seed]"""
+Run on a box without a GPU:  python tests/fuzz_worker.py [rounds] [first_seed]"""
 import os
 import sys
 
