@@ -182,7 +182,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline; never the product path)
 # ---------------------------------------------------------------------------------------------------
-def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None):
+def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None, ready=None):
     """Times the oracle on the same workload.  Returns (per-step seconds, per-stage seconds of the last step).
     `budget_s` bounds the CPU work: once it is used up the loop stops after the next timed pass (warm-up passes that no
     longer fit are skipped), so a large --steps cannot turn the reference arm into a run of many minutes."""
@@ -230,6 +230,8 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None):
     if workload == "climate":
         eroded = pre.copy()
         oracle.run_post_processing(mesh, xyz, eroded, SLIDERS, nd, SEED, hot, hiters)
+    if ready is not None:
+        ready()                      # preparation done: several of these run side by side and start their passes together
     times, stages = [], {}
     began, over = time.perf_counter(), False
     for i in range(warmup + steps):
@@ -278,6 +280,30 @@ def run_reference(args):
     v = n * len(times) / total
     sample = (f"{args.workload} workload, {len(times)} timed passes of {n} cells (of {args.steps} requested; the arm stops after "
               f"≈150 s of CPU work), oracle/ C++ -O2, 1 thread")
+    # the counterpart of the own arm's `throughput_in_flight`: the same number of planets at once, one host thread each
+    in_flight = None
+    if args.workload == "full" and args.in_flight > 1:
+        import threading
+        b = min(args.in_flight, os.cpu_count() or 1)
+        errs, mark = [], {}
+        gate = threading.Barrier(b, action=lambda: mark.setdefault("t0", time.perf_counter()))
+
+        def one():
+            try:
+                oracle_step_seconds(inp, args.hiters, 1, 0, args.workload, ready=gate.wait)
+            except Exception as e:
+                errs.append(e)
+                gate.abort()
+
+        threads = [threading.Thread(target=one) for _ in range(b)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        secs = time.perf_counter() - mark.get("t0", time.perf_counter())
+        if not errs:
+            in_flight = {"planets_in_flight": b, "cores": b, "value": n * b / secs, "unit": UNIT, "seconds": secs,
+                         "note": "one oracle pipeline per host thread, one pass each"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -288,6 +314,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages_last_step": stages},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "throughput_in_flight": in_flight,
     }), flush=True)
 
 
