@@ -275,11 +275,11 @@ def run_reference(args):
         return
     inp = Inputs(args.cells)
     n = inp.mesh.numRegions
-    times, stages = oracle_step_seconds(inp, args.hiters, args.steps, args.warmup, args.workload, budget_s=150.0)
+    times, stages = oracle_step_seconds(inp, args.hiters, args.steps, args.warmup, args.workload, budget_s=120.0)
     total = float(np.sum(times))
     v = n * len(times) / total
     sample = (f"{args.workload} workload, {len(times)} timed passes of {n} cells (of {args.steps} requested; the arm stops after "
-              f"≈150 s of CPU work), oracle/ C++ -O2, 1 thread")
+              f"≈120 s of CPU work), oracle/ C++ -O2, 1 thread")
     # the counterpart of the own arm's `throughput_in_flight`: the same number of planets at once, one host thread each
     in_flight = None
     if args.workload == "full" and args.in_flight > 1:
