@@ -256,9 +256,9 @@ pb_status pb_generate_coarse_plates(pb_context* ctx, double seed, int32_t numPla
  * receive the CSR neighbour lists of the spherical Delaunay triangulation (= convex hull), each row in the
  * reference's circulation order `s = next(halfedges[s])` for the canonical triangle numbering described in
  * csrc/pb_meshgen.h.  Arrays follow the context's pointer mode.  PB_ERR_INVALID when the points do not give a closed
- * triangulated sphere (duplicates, fewer than 4 points), when a region has more than 32 neighbours, or when the point
- * density varies by orders of magnitude over the sphere (the candidate search is sized for the mean spacing; the
- * reference's jittered Fibonacci points, uniform random points and moderate clusters are all fine).
+ * triangulated sphere (duplicates, fewer than 4 points) or when a region has more than 32 neighbours.  The candidate
+ * search is sized for the mean spacing; point sets whose density varies by orders of magnitude are still triangulated
+ * (the search block of the affected regions grows up to the whole sphere), only slowly.
  * pb_mesh_create_from_points = pb_triangulate_sphere + pb_mesh_create without the round trip through the host;
  * pb_mesh_get_adjacency returns the CSR arrays of a mesh (host pointers).
  * pb_generate_fibonacci_sphere replaces generateFibonacciSphere (js/sphere-mesh.js:9-37, jitter draws from

@@ -252,6 +252,42 @@ struct MeshGenInvertK {
     PB_DEV void operator()(int j) const { pos[sid[j]] = j; }
 };
 
+// Second chance for the stars StarK could not close within its block limit (point sets whose density varies by orders of
+// magnitude): the block keeps growing until it is the whole grid.  Launched only when the count pass reports failures, so
+// evenly spread points — every planet the reference generates — never run it.  mode 0: degree; mode 1: row into adj.
+struct StarRetryK {
+    StarK star; const int* pos; uint8_t* retried; int mode;
+    PB_DEV void operator()(int me) const {
+        if (mode == 0 ? star.deg[me] != 0 : !retried[me]) return;
+        const int j = pos[me];
+        const P3 r = star.pt(j);
+        const GridSpec& g = star.g;
+        const int ix = g.coord(r.x), iy = g.coord(r.y), iz = g.coord(r.z);
+        int ring[kMaxRing];
+        int d = -1;
+        for (int L = kMaxBlock + 1; d < 0; L += (L >> 1)) {
+            const bool whole = L >= g.G - 1;
+            d = star.wrap(j, r, ix, iy, iz, whole ? g.G : L, ring, whole);
+            if (whole) break;
+        }
+        if (d < 3) { if (mode == 0) atomic_add(star.fail, 1); return; }
+        if (mode == 0) { star.deg[me] = d; retried[me] = 1; return; }
+        int ids[kMaxRing];
+        for (int i = 0; i < d; i++) ids[i] = star.sid[ring[i]];
+        int bi = 0, b0 = 0, b1 = 0, b2 = 0;                       // same canonical start as StarK
+        for (int i = 0; i < d; i++) {
+            const int u = ids[i], v = ids[i + 1 == d ? 0 : i + 1];
+            int t0, t1, t2;
+            if (me < u && me < v) { t0 = me; t1 = u; t2 = v; }
+            else if (u < v) { t0 = u; t1 = v; t2 = me; }
+            else { t0 = v; t1 = me; t2 = u; }
+            if (i == 0 || t0 < b0 || (t0 == b0 && (t1 < b1 || (t1 == b1 && t2 < b2)))) { bi = i; b0 = t0; b1 = t1; b2 = t2; }
+        }
+        int* row = star.adj + star.off[me];
+        for (int k = 0; k < d; k++) { int i = bi - k; if (i < 0) i += d; row[k] = ids[i]; }
+    }
+};
+
 // adjacency must be symmetric: every edge r→q has its twin q→r
 struct MeshGenSymmetryK {
     int n; const int* off; const int* adj; int* bad;
@@ -321,7 +357,7 @@ struct SphereTriangulator {
     DevBuf<uint32_t> key;
     DevBuf<int> sid, deg, fail, rows, pos;
     DevBuf<double> sx, sy, sz;
-    DevBuf<uint8_t> scanTemp;
+    DevBuf<uint8_t> scanTemp, retried;
     Prims prims;
 
     static GridSpec grid_for(int n) {
@@ -369,9 +405,22 @@ struct SphereTriangulator {
         dev_copy(h, fail.p, 2 * sizeof(int), 1, ex.stream);
         dev_copy(&total, dOff + n, sizeof(int), 1, ex.stream);
         stream_sync(ex.stream);
-        if (h[0]) throw Error("spherical Delaunay: " + std::to_string(h[0]) + " region stars could not be closed (duplicate points, a region with more than 32 neighbours, or a point density that varies by orders of magnitude)");
+        bool anyRetried = false;
+        if (h[0] && !getenv("PB_MESH_NO_RETRY")) {     // some blocks never got large enough: grow them up to the whole grid
+            anyRetried = true;
+            dev_memset(retried.ensure(n), 0, (size_t)n, ex.stream);
+            dev_memset(fail.p, 0, sizeof(int), ex.stream);
+            ex.for_each(n, StarRetryK{StarK{n, g, key.p, sid.p, sx.p, sy.p, sz.p, deg.p, rows.p, nullptr, nullptr, fail.p}, pos.p, retried.p, 0});
+            exclusive_scan(ex, deg.p, dOff, n + 1);
+            dev_copy(h, fail.p, 2 * sizeof(int), 1, ex.stream);
+            dev_copy(&total, dOff + n, sizeof(int), 1, ex.stream);
+            stream_sync(ex.stream);
+        }
+        if (h[0]) throw Error("spherical Delaunay: " + std::to_string(h[0]) + " region stars could not be closed (duplicate points or a region with more than 32 neighbours)");
         if (total != 6 * n - 12) throw Error("spherical Delaunay: edge count " + std::to_string(total) + " != 6n-12 (degenerate point set)");
         ex.for_each(n, StarFillK{StarK{n, g, key.p, sid.p, sx.p, sy.p, sz.p, deg.p, rows.p, dOff, dAdj, fail.p}, pos.p});
+        if (anyRetried)
+            ex.for_each(n, StarRetryK{StarK{n, g, key.p, sid.p, sx.p, sy.p, sz.p, deg.p, rows.p, dOff, dAdj, fail.p}, pos.p, retried.p, 1});
         ex.for_each(n, MeshGenSymmetryK{n, dOff, dAdj, fail.p + 2});
         dev_copy(h, fail.p, 3 * sizeof(int), 1, ex.stream);
         stream_sync(ex.stream);

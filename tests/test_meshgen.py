@@ -148,3 +148,25 @@ def test_triangles_and_halfedges_match_hull(backend, n, seed):
     want_e = (((e[t[:, 0]] + e[t[:, 1]]) + e[t[:, 2]]) / 3).astype(np.float32)
     assert (dm.computeTriangleElevations(elev).view(np.uint32) == want_e.view(np.uint32)).all()
     dm.close()
+
+
+def test_extreme_density_contrast_uses_the_retry_path(emu_lib):
+    """9 of 10 points inside a 0.6° cap: the stars of the sparse regions do not close within the normal block limit and go
+    through StarRetryK (block grown to the whole grid).  Host emulation only so far — the retry kernel has not run on a GPU."""
+    rng = np.random.default_rng(16663996)
+    p = rng.normal(size=(5000, 3)) * 0.01 + np.array([0, 0, 1.0])
+    q = rng.normal(size=(500, 3))
+    pts = np.concatenate([p, q])
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    mesh, xyz = _hull(pts.astype(np.float32).reshape(-1))
+    import os
+    from planet_heightmap_generation_b200 import PlanetB200Error
+    os.environ["PB_MESH_NO_RETRY"] = "1"
+    try:
+        with pytest.raises(PlanetB200Error, match="could not be closed"):      # the normal block limit is not enough here
+            DeviceMesh.from_points(xyz, lib=emu_lib)
+    finally:
+        del os.environ["PB_MESH_NO_RETRY"]
+    dm = DeviceMesh.from_points(xyz, lib=emu_lib)
+    _check_same(dm, mesh)
+    dm.close()
