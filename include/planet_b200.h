@@ -55,9 +55,11 @@ const char* pb_version(void);
 pb_status pb_set_stream(pb_context* ctx, void* cuda_stream);
 pb_status pb_set_pointer_mode(pb_context* ctx, int mode);
 pb_status pb_synchronize(pb_context* ctx);
-/* Engine options (name, value).  "flood": "device" (default — the heap flood of priorityFloodCarve runs as a
- * one-CTA CUDA kernel) or "host" (that one serial pass runs on a host core; everything else stays on the GPU;
- * results are identical). */
+/* Engine options (name, value).  "flood": where pass 1 of priorityFloodCarve (js/terrain-post.js:131-147) runs —
+ * one serial chain of heap pops whose tie order depends on the heap layout.  "host" (default): on a host core, like
+ * the other host-serial stages (assignDistanceField); "device": the one-CTA CUDA kernel k_flood_heap (≈ 8x slower:
+ * a single warp retires the dependent chain at ~0.1 instructions per cycle).  Everything else of the function stays
+ * on the GPU either way and the results are identical. */
 pb_status pb_set_option(pb_context* ctx, const char* name, const char* value);
 /* kernels launched by this library on any context since process start (bench: gpu_launches) */
 int64_t pb_launch_count(void);

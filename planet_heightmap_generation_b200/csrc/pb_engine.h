@@ -3,6 +3,7 @@
 // js/terrain-post.js).  All state that the reference allocates per call as typed arrays lives in
 // mesh-owned device buffers that are reused between calls.
 #pragma once
+#include <chrono>
 #include "pb_platform.h"
 #include "pb_noise.h"
 #include "pb_stencil.h"
@@ -19,7 +20,7 @@ inline double js_round(double x) { return floor(x + 0.5); }   // Math.round
 struct Context {
     int device = 0;
     int pointerMode = PB_POINTER_HOST;
-    bool floodOnHost = false;      // option "flood=host": run the serial heap flood on a host core
+    bool floodOnHost = true;       // option "flood": "host" (default) = the serial heap pass of priorityFloodCarve on a host core, "device" = k_flood_heap
     Exec ex;
     DevBuf<int> ticket;
     Profiler profiler;
@@ -272,6 +273,34 @@ struct Mesh {
         if (src != elev) dev_copy(elev, src, sizeof(float) * (size_t)N, 2, ex().stream);
     }
 
+    // pass 1 on one host core (the default, pb_flood.h): elev / key0 / drainTo / visited / seeds come down over PCIe
+    // into pinned buffers (13 B/cell), surface and drainTo go back up (8 B/cell)
+    PinnedBuf<float> hfElev, hfSurface, hfKey0;
+    PinnedBuf<int> hfDrain, hfSeeds;
+    PinnedBuf<uint8_t> hfVisited;
+    std::vector<HostHeapEntry> hfHeap;
+    double lastFloodHostMs = 0;
+    void flood_heap_on_host(const float* elev) {
+        const Exec& x = ex();
+        hfElev.ensure(N); hfSurface.ensure(N); hfKey0.ensure(N); hfDrain.ensure(N); hfVisited.ensure(N); hfSeeds.ensure(N);
+        int nSeeds = 0;
+        dev_copy(&nSeeds, counters.p + 0, sizeof(int), 1, x.stream);
+        dev_copy(hfElev.data(), elev, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfKey0.data(), key.p, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfDrain.data(), drainTo.p, sizeof(int) * (size_t)N, 1, x.stream);
+        dev_copy(hfVisited.data(), visited.p, (size_t)N, 1, x.stream);
+        dev_copy(hfSeeds.data(), seeds.p, sizeof(int) * (size_t)N, 1, x.stream);   // nSeeds is not known yet: the list is ≤ N ints
+        stream_sync(x.stream);
+        memcpy(hfSurface.data(), hfElev.data(), sizeof(float) * (size_t)N);         // surface starts as a copy of the elevation (:107)
+        const auto t0 = std::chrono::steady_clock::now();
+        flood_heap_host(N, hOffCopy.data(), hAdjCopy.data(), hfElev.data(), hfSurface.data(), hfKey0.data(), hfDrain.data(),
+                        hfVisited.data(), hfSeeds.data(), nSeeds, hfHeap);
+        lastFloodHostMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (getenv("PB_DEBUG")) fprintf(stderr, "[pb] flood pass 1 on the host: %d seeds, %.2f ms\n", nSeeds, lastFloodHostMs);
+        dev_copy(surface.p, hfSurface.data(), sizeof(float) * (size_t)N, 0, x.stream);
+        dev_copy(drainTo.p, hfDrain.data(), sizeof(int) * (size_t)N, 0, x.stream);
+        stream_sync(x.stream);
+    }
 #if PB_CUDA
     // pass 1 on one CTA: shared-memory heap + visited bitmap (pb_flood.h)
     DevBuf<HeapEntry> heapSpill;
@@ -298,29 +327,6 @@ struct Mesh {
             lastMaxHeap = read_int(counters.p + 12);
             fprintf(stderr, "[pb] flood: max heap %d (%d entries fit in shared memory)\n", lastMaxHeap, cap);
         }
-    }
-    // option flood=host: the serial pass on one host core (arrays round-trip over PCIe, ~17 B/cell)
-    std::vector<float> hfElev, hfSurface, hfKey0, hfKey;
-    std::vector<int> hfDrain, hfSeeds, hfHeap;
-    std::vector<uint8_t> hfVisited;
-    void flood_heap_on_host(const float* elev) {
-        const Exec& x = ex();
-        hfElev.resize(N); hfSurface.resize(N); hfKey0.resize(N); hfDrain.resize(N); hfVisited.resize(N); hfSeeds.resize(N);
-        int nSeeds = 0;
-        dev_copy(&nSeeds, counters.p + 0, sizeof(int), 1, x.stream);
-        dev_copy(hfElev.data(), elev, sizeof(float) * (size_t)N, 1, x.stream);
-        dev_copy(hfSurface.data(), surface.p, sizeof(float) * (size_t)N, 1, x.stream);
-        dev_copy(hfKey0.data(), key.p, sizeof(float) * (size_t)N, 1, x.stream);
-        dev_copy(hfDrain.data(), drainTo.p, sizeof(int) * (size_t)N, 1, x.stream);
-        dev_copy(hfVisited.data(), visited.p, (size_t)N, 1, x.stream);
-        stream_sync(x.stream);
-        dev_copy(hfSeeds.data(), seeds.p, sizeof(int) * (size_t)nSeeds, 1, x.stream);
-        stream_sync(x.stream);
-        flood_heap_host(N, hOffCopy.data(), hAdjCopy.data(), hfElev.data(), hfSurface.data(), hfKey0.data(), hfDrain.data(),
-                        hfVisited.data(), hfSeeds.data(), nSeeds, hfHeap, hfKey);
-        dev_copy(surface.p, hfSurface.data(), sizeof(float) * (size_t)N, 0, x.stream);
-        dev_copy(drainTo.p, hfDrain.data(), sizeof(int) * (size_t)N, 0, x.stream);
-        stream_sync(x.stream);
     }
     // pass 2: binary lifting over the flood forest, one CTA per flood tree (pb_flood.h)
     void carve_lift_cuda(float* elev, const uint8_t* isOcean, double carveStrength) {
@@ -367,12 +373,14 @@ struct Mesh {
         counters.ensure(16);
         seeds.ensure(N); heap.ensure(N);
         prims.compact_flagged(x, seedFlag.p, N, seeds.p, counters.p + 0);
-#if PB_CUDA
         if (ctx->floodOnHost) flood_heap_on_host(elev);
-        else flood_heap_cuda(elev);
+        else {
+#if PB_CUDA
+            flood_heap_cuda(elev);
 #else
-        x.single(FloodSerialK{g, elev, surface.p, key.p, drainTo.p, visited.p, seeds.p, counters.p + 0, heap.p});
+            x.single(FloodSerialK{g, elev, surface.p, key.p, drainTo.p, visited.p, seeds.p, counters.p + 0, heap.p});
 #endif
+        }
         if (taps) {
             if (taps->drainTo) dev_copy(taps->drainTo, drainTo.p, sizeof(int) * (size_t)N, 2, x.stream);
             if (taps->surface) dev_copy(taps->surface, surface.p, sizeof(float) * (size_t)N, 2, x.stream);

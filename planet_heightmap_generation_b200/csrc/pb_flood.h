@@ -164,65 +164,79 @@ struct FloodSerialK {
     }
 };
 
-// Host form of pass 1 (plain C++, both builds).  The CUDA engine can run this stage on a host core
-// instead of the one-CTA kernel (context option "flood=host"): the pass is one serial chain of heap
-// operations, which a CPU core executes ~6x faster than a single GPU warp.  Same MinHeap semantics.
+// Host form of pass 1 (plain C++, both builds) — the engine's default for this pass.  The pass is ONE serial
+// chain of |land| heap operations whose tie order between equal f32 keys depends on the binary-heap layout
+// (SURVEY.md A.5), so it has to be replayed operation by operation; a CPU core retires that dependent chain
+// ~8x faster than a single GPU warp (profiles/r01_flood_heap_ncu.md: ≈ 430 dependent instructions per pop at
+// ≈ 9.5 cycles each on the SM).  Like assignDistanceField it is therefore a host-serial stage of the engine
+// (class S with a data-dependent global order); "flood=device" selects the one-CTA kernel k_flood_heap instead.
+// Same MinHeap semantics as js/terrain-post.js:12-47: sift-up stops on >=, sift-down prefers the left child on
+// ties.  The heap stores (key, cell) pairs — keys never change once pushed — with node j in slot j+1 so the two
+// children of a node share one aligned 16-byte word.
+struct HostHeapEntry { float k; int c; };
 inline void flood_heap_host(int N, const int* off, const int* adj, const float* elev, float* surface, const float* key0,
-                            int* drainTo, uint8_t* visited, const int* seeds, int nSeeds, std::vector<int>& heap,
-                            std::vector<float>& key) {
-    key.assign(key0, key0 + N);
-    heap.clear();
-    auto push = [&](int cell) {
-        heap.push_back(cell);
-        size_t i = heap.size() - 1;
-        const float kc = key[cell];
+                            int* drainTo, uint8_t* visited, const int* seeds, int nSeeds, std::vector<HostHeapEntry>& heapBuf) {
+    if ((int)heapBuf.size() < N + 4) heapBuf.resize((size_t)N + 4);
+    HostHeapEntry* h = heapBuf.data() + 1;             // node j at h[j]; h[-1] unused (keeps sibling pairs 16-byte aligned)
+    size_t n = 0;
+    auto push = [&](float kc, int cell) {
+        size_t i = n++;
         while (i > 0) {
             const size_t p = (i - 1) >> 1;
-            const int pc = heap[p];
-            if (kc >= key[pc]) break;
-            heap[i] = pc; heap[p] = cell;
+            const HostHeapEntry pe = h[p];
+            if (kc >= pe.k) break;                      // MinHeap.push :22
+            h[i] = pe;
             i = p;
         }
+        h[i].k = kc; h[i].c = cell;
     };
-    for (int s = 0; s < nSeeds; s++) push(seeds[s]);
-    while (!heap.empty()) {
-        const int r = heap[0];
-        const int last = heap.back();
-        heap.pop_back();
-        const size_t n = heap.size();
-        if (n > 0) {
-            heap[0] = last;
-            const float kl = key[last];
+    for (int s = 0; s < nSeeds; s++) push(key0[seeds[s]], seeds[s]);
+    while (n > 0) {
+        const int r = h[0].c;
+        const HostHeapEntry last = h[--n];
+        if (n > 0) {                                    // MinHeap.pop :27-46 — last → root, sift down (left child wins ties)
+            h[n].k = INFINITY;                          // sentinel: a missing right child never wins (strict <), no bounds test on it
             size_t i = 0;
             for (;;) {
-                size_t smallest = i; float ks = kl;
-                const size_t l = 2 * i + 1, rr = l + 1;
-                if (l < n) { const float k = key[heap[l]]; if (k < ks) { smallest = l; ks = k; } }
-                if (rr < n) { const float k = key[heap[rr]]; if (k < ks) { smallest = rr; ks = k; } }
-                if (smallest == i) break;
-                heap[i] = heap[smallest]; heap[smallest] = last;
-                i = smallest;
+                const size_t l = 2 * i + 1;
+                if (l >= n) break;
+                const float kl = h[l].k, kr = h[l + 1].k;
+                const size_t m = l + (kr < kl ? 1 : 0);          // branch-free child choice: the direction is unpredictable
+                const float km = kr < kl ? kr : kl;
+                if (!(km < last.k)) break;
+                h[i] = h[m];
+                i = m;
             }
+            h[i] = last;
+#if defined(__GNUC__)
+            {   // the new root is the likely next pop: pull its row and its neighbours' flags towards the core
+                const int c2 = h[0].c;
+                __builtin_prefetch(adj + off[c2], 0, 1);
+                __builtin_prefetch(visited + c2, 0, 1);
+            }
+#endif
         }
         const double surfR = surface[r];
+        const double lim = surfR + PB_FLOOD_EPS;
         for (int j = off[r], e = off[r + 1]; j < e; j++) {
             const int nb = adj[j];
             if (visited[nb]) continue;
             visited[nb] = 1;
             drainTo[nb] = r;
-            if ((double)elev[nb] < surfR + PB_FLOOD_EPS) {
-                const float s = (float)(surfR + PB_FLOOD_EPS);
+            float kn = key0[nb];
+            if ((double)elev[nb] < lim) {
+                const float s = (float)lim;
                 surface[nb] = s;
-                // key0 = f32(elev + noise) is not enough here: recompute from the filled surface
+                // key0 = f32(elev + noise) is not enough here: recompute from the filled surface (cellNoise :100-105)
                 const double p1 = (double)nb * 2654435761.0;
-                uint32_t h = (uint32_t)(unsigned long long)p1;
-                const int32_t x1 = (int32_t)((h >> 16) ^ h);
+                uint32_t hh = (uint32_t)(unsigned long long)p1;
+                const int32_t x1 = (int32_t)((hh >> 16) ^ hh);
                 const double p2 = (double)x1 * 73244475.0;
-                h = (uint32_t)(unsigned long long)(long long)p2;
-                h = (h >> 16) ^ h;
-                key[nb] = (float)((double)s + ((double)h / 4294967295.0) * 0.01);
+                hh = (uint32_t)(unsigned long long)(long long)p2;
+                hh = (hh >> 16) ^ hh;
+                kn = (float)((double)s + ((double)hh / 4294967295.0) * 0.01);
             }
-            push(nb);
+            push(kn, nb);
         }
     }
 }

@@ -121,6 +121,45 @@ struct DevBuf {
     operator T*() const { return p; }
 };
 
+// Page-locked host buffer for the arrays of the host-serial stages (flood pass 1, randomized fills): they
+// cross PCIe at full rate and asynchronously to the host thread.
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
+    void release() {
+        if (!p) return;
+#if PB_CUDA
+        cudaFreeHost(p);
+#else
+        free(p);
+#endif
+        p = nullptr; cap = 0;
+    }
+    T* ensure(size_t n) {
+        if (n > cap) {
+            release();
+            if (n == 0) n = 1;
+#if PB_CUDA
+            void* q = nullptr;
+            PB_CUDA_CHECK(cudaMallocHost(&q, n * sizeof(T)));
+            p = (T*)q;
+#else
+            p = (T*)malloc(n * sizeof(T));
+            if (!p) throw Error("malloc failed");
+#endif
+            cap = n;
+        }
+        return p;
+    }
+    T* data() const { return p; }
+    T& operator[](size_t i) const { return p[i]; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // device-side primitives
 // ---------------------------------------------------------------------------------------------

@@ -87,16 +87,17 @@ def test_priority_flood_carve_large(oracle, cuda_lib):
     assert_bit_equal(got, want, "priorityFloodCarve elevation")
 
 
-@pytest.mark.gpu
-def test_flood_on_host_option_matches(oracle, cuda_lib, planet_medium):
-    """Option flood=host (the serial heap pass on a host core, the rest on the GPU) gives identical results."""
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_flood_option_host_and_device_match(backend, oracle, planet_medium, where):
+    """Option flood=host (default: the serial heap pass on a host core, the rest on the GPU) and flood=device (the
+    one-CTA kernel k_flood_heap; on the emulation the sequential form of that kernel) give the oracle's bits."""
     from planet_heightmap_generation_b200.terrain_post import priorityFloodCarve
     mesh, xyz, nd, elev = planet_medium()
     ocean = (elev <= 0).astype(np.uint8)
     want = elev.copy()
     o_drain, o_surf, o_open = oracle.priority_flood_carve(mesh, want, ocean, 0.5)
-    dm = _dm(cuda_lib, mesh, xyz)
-    dm.set_option("flood", "host")
+    dm = _dm(backend, mesh, xyz)
+    dm.set_option("flood", where)
     got = elev.copy()
     drain, surf, openo = priorityFloodCarve(dm, got, ocean, 0.5, taps=True)
     assert_bit_equal(drain, o_drain, "drainTo")
