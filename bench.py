@@ -114,8 +114,30 @@ def workload_name(cells, hiters, workload):
             f"projectCoarsePlates + smoothAndReconnectPlates(3) + buildSuperPlates")
     tri = "buildSphere (Fibonacci points with seeded jitter + pole, spherical Delaunay adjacency in the SphereMesh constructor's order)"
     what = {"post": post, "climate": clim, "elevation": elev, "mesh": tri, "plates": plat,
+            "elevation+post": " then ".join([elev, post]),
             "full": " then ".join([tri, plat, elev, post, clim])}[workload]
     return f"{cells + 1}-cell Fibonacci sphere (jitter 0.75, seed {SEED}), {what}"
+
+
+def bench_config(args, world):
+    """`config` of the JSON line — the same dict in both arms (it depends on the command line only)."""
+    return {"workload": workload_name(args.cells, args.hiters, args.workload), "cells_per_planet": args.cells + 1,
+            "seed": SEED, "hiters": args.hiters,
+            "multi_gpu": "single" if world == 1 else MULTI_GPU_TEXT[args.multi_gpu],
+            "l2": "256 MiB buffer written between steps (inside the timed region)",
+            "flood": args.flood or "host",
+            "inputs": "only (N, jitter, seed) and the slider defaults: points, mesh adjacency, coarse plates, r_plate and "
+                      "super plates are rebuilt inside every step",
+            "cpu_arm": "oracle/ (C++ -O2 restatement of the reference's JS, one thread like its single Web Worker); it starts from "
+                       "the finished mesh: mesh construction is in the GPU arm's step only (its CPU checker is qhull, not the "
+                       "reference's Delaunator)"}
+
+
+MULTI_GPU_TEXT = {
+    "replicas": "replicas (one copy of the planet per GPU, no data-path collective)",
+    "shards": "cell-range shards, one-cell halo: every rank holds the planet, the Jacobi / propagation sweep loops of the climate "
+              "stack run on contiguous cell-id ranges with a peer-memory halo exchange per sweep; class S/R stages replicated",
+}
 
 
 CLIMATE_REPLY_F32 = (  # the per-cell arrays of the worker's climateDone reply (js/planet-worker.js:635-653)
@@ -182,10 +204,11 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (the oracle is the checker / baseline; never the product path)
 # ---------------------------------------------------------------------------------------------------
-def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None, ready=None):
+def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None, ready=None, keep=None):
     """Times the oracle on the same workload.  Returns (per-step seconds, per-stage seconds of the last step).
     `budget_s` bounds the CPU work: once it is used up the loop stops after the next timed pass (warm-up passes that no
-    longer fit are skipped), so a large --steps cannot turn the reference arm into a run of many minutes."""
+    longer fit are skipped), so a large --steps cannot turn the reference arm into a run of many minutes.
+    `keep` (a dict) receives the result arrays of the last pass — the checker side of the bench's parity block."""
     from oracle import binding as oracle
     oracle.build()
     mesh, xyz = inp.mesh, inp.xyz
@@ -227,6 +250,7 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None, rea
     pre = hot = eroded = None
     if workload in ("post", "climate"):
         pre, hot = elevation()
+        pre, hot = pre.copy(), hot.copy()
     if workload == "climate":
         eroded = pre.copy()
         oracle.run_post_processing(mesh, xyz, eroded, SLIDERS, nd, SEED, hot, hiters)
@@ -240,15 +264,27 @@ def oracle_step_seconds(inp, hiters, steps, warmup, workload, budget_s=None, rea
         if workload in ("full", "plates"):
             plates()
         t0 = time.perf_counter()
-        if workload in ("full", "elevation"):
+        if workload in ("full", "elevation", "elevation+post"):
             e, h = elevation()
         t1 = time.perf_counter()
-        if workload in ("full", "post"):
-            oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, h, hiters)
+        if keep is not None and e is not None:
+            keep["prePostElev"] = e.copy()
+        if workload in ("full", "post", "elevation+post"):
+            o_delta, o_ocean = oracle.run_post_processing(mesh, xyz, e, SLIDERS, nd, SEED, h, hiters)
+            if keep is not None:
+                keep.update(erosionDelta=o_delta, r_isOcean=o_ocean)
         t2 = time.perf_counter()
         if workload in ("full", "climate"):
-            clim.run_all(eroded if workload == "climate" else e, pstate["pio"], pstate["r_plate"], SEED)
+            o_koppen = clim.run_all(eroded if workload == "climate" else e, pstate["pio"], pstate["r_plate"], SEED)
+            if keep is not None:
+                keep["r_koppen"] = o_koppen
+                for k in CLIMATE_REPLY_F32:
+                    keep[k] = clim.get(k)
         t3 = time.perf_counter()
+        if keep is not None:
+            keep.update(r_plate=pstate["r_plate"].copy(), r_superPlate=np.asarray(pstate["r_super"]).copy())
+            if e is not None:
+                keep["r_elevation"] = e if workload != "climate" else eroded
         if i >= warmup or over:
             times.append(t3 - t)
         stages = {"plates_s": t0 - t, "elevation_s": t1 - t0, "post_s": t2 - t1, "climate_s": t3 - t2}
@@ -275,7 +311,7 @@ def run_reference(args):
         return
     inp = Inputs(args.cells)
     n = inp.mesh.numRegions
-    times, stages = oracle_step_seconds(inp, args.hiters, args.steps, args.warmup, args.workload, budget_s=120.0)
+    times, stages = oracle_step_seconds(inp, args.hiters, args.steps, min(args.warmup, 1), args.workload, budget_s=120.0)
     total = float(np.sum(times))
     v = n * len(times) / total
     sample = (f"{args.workload} workload, {len(times)} timed passes of {n} cells (of {args.steps} requested; the arm stops after "
@@ -305,12 +341,12 @@ def run_reference(args):
             in_flight = {"planets_in_flight": b, "cores": b, "value": n * b / secs, "unit": UNIT, "seconds": secs,
                          "note": "one oracle pipeline per host thread, one pass each"}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.cells, args.hiters, args.workload),
-                   "note": "reference is browser JavaScript (one Web Worker, single thread); no JS runtime in this image, "
-                           "so this arm times oracle/ — the C++ -O2 restatement of the same functions — on one host core"},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1000 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+        "note": "reference is browser JavaScript (one Web Worker, single thread); no JS runtime in this image, "
+                "so this arm times oracle/ — the C++ -O2 restatement of the same functions — on one host core",
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages_last_step": stages},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -461,7 +497,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     wl = args.workload
-    do_elev, do_post, do_clim = wl in ("full", "elevation"), wl in ("full", "post"), wl in ("full", "climate")
+    do_elev, do_post, do_clim = wl in ("full", "elevation", "elevation+post"), wl in ("full", "post", "elevation+post"), wl in ("full", "climate")
     do_mesh = wl in ("full", "mesh")
     do_plates = wl in ("full", "plates")
     # replicas: every rank processes its own copy of the same seeded planet (identical work per GPU, so the
@@ -611,7 +647,7 @@ def run_b200(args):
 
     host_stage = {}
 
-    def step_host():
+    def step_host(collect=False):
         flush.zero_()
         np_elev, np_hot = h_elev.numpy(), h_hot0.numpy()
         tt = [time.perf_counter()]
@@ -629,6 +665,8 @@ def run_b200(args):
         elif do_post:
             h_elev.copy_(h_pre)
         tt.append(time.perf_counter())
+        if collect and (do_elev or do_post):
+            host["prePostElev"] = np.array(np_elev, copy=True)
         if do_post:
             runPostProcessing(dm, None, np_elev, SLIDERS, None, SEED, np_hot, hItersOverride=args.hiters,
                               out_erosionDelta=np_delta, out_isOcean=np_ocean, timing=False)
@@ -700,15 +738,42 @@ def run_b200(args):
     roofline = roof(dominant)
     roofline_sweep = roof(sweep_kernel) if sweep_kernel != dominant else None
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        times, stages = oracle_step_seconds(inp, args.hiters, 1, 0, wl)
+        keep = {}
+        times, stages = oracle_step_seconds(inp, args.hiters, 1, 0, wl, keep=keep)
         cpu_baseline = {"value": N / times[0], "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": f"one full pass of the same {N}-cell workload ({times[0]:.1f} s), oracle/ C++ -O2, 1 thread"
                                   + ("; mesh construction is not in the CPU figure (its checker is qhull, not the reference's "
                                      "Delaunator: `--workload mesh` times it separately)" if wl == "full" else
                                      " (qhull convex hull + SphereMesh constructor, scipy)" if wl == "mesh" else ""),
                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "stages": stages}
+        # ---- parity on the benchmark's own planet: every array of the timed arm's reply against the oracle's, bit for bit ----
+        step_host(collect=True)
+        got = {"r_plate": np_plate if do_plates else r_plate_dev_final.cpu().numpy(),
+               "r_superPlate": np_super if do_plates else r_super_dev_final.cpu().numpy()}
+        if do_elev or do_post:
+            got["prePostElev"] = host.get("prePostElev")
+        if do_elev or do_post or do_clim:
+            got["r_elevation"] = host["elev"]
+        if do_post:
+            got.update(erosionDelta=np_delta, r_isOcean=np_ocean)
+        if do_clim:
+            got["r_koppen"] = np_koppen
+            got.update({k: reply[k] for k in CLIMATE_REPLY_F32})
+        fields = {}
+        for k, want in keep.items():
+            if k not in got or got[k] is None:
+                continue
+            a, b_ = np.ascontiguousarray(got[k]), np.ascontiguousarray(want)
+            if a.shape != b_.shape or a.dtype != b_.dtype:
+                fields[k] = int(max(a.size, b_.size))
+                continue
+            fields[k] = int(((a.view(np.uint32) != b_.view(np.uint32)) if a.dtype == np.float32 else (a != b_)).sum())
+        parity = {"vs": "oracle", "cells": N, "fields": fields, "mismatches": int(sum(fields.values())),
+                  "compare": "bit-exact (f32 compared as uint32), arrays of one extra untimed pass through the host-pointer C ABI "
+                             "against one pass of oracle/ on the same (N, seed, sliders)"}
+        log(f"[bench] parity vs oracle at {N} cells: {parity['mismatches']} mismatching cells over {len(fields)} arrays")
 
     # ---- several planets in flight (supplementary: `value` above is one planet at a time) ----------------------
     in_flight = None
@@ -729,13 +794,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.cells, args.hiters, wl), "cells_per_gpu": N,
-                       "multi_gpu": "replicas (one copy of the planet per GPU, no data-path collective)" if world > 1 else "single",
-                       "l2": "256 MiB buffer written between steps (inside the timed region)",
-                       "land_cells": land,
-                       "flood": args.flood or "device",
-                       "inputs": "only (N, jitter, seed) and the slider defaults: points, mesh adjacency, coarse plates, r_plate and "
-                                 "super plates are rebuilt inside every step"},
+            "impl": "b200", "config": bench_config(args, world), "land_cells": land, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
@@ -744,6 +803,8 @@ def run_b200(args):
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and parity["mismatches"]:
+        raise SystemExit(f"bench.py: the timed arm's results differ from the oracle: {parity['fields']}")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -838,11 +899,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "mesh", "plates", "sharded-sweeps"])
+    ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "elevation+post", "mesh", "plates", "sharded-sweeps"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],
-                    help="engine option: where the serial heap pass of priorityFloodCarve runs (default device)")
+                    help="engine option: where the serial heap pass of priorityFloodCarve runs (default host)")
+    ap.add_argument("--multi-gpu", default="replicas", choices=["replicas", "shards"], dest="multi_gpu",
+                    help="N>1: independent planets per GPU (weak) or one planet with cell-range sharded sweep loops (strong)")
     ap.add_argument("--in-flight", type=int, default=4, dest="in_flight",
                     help="planets kept in flight per GPU for the supplementary throughput figure of the full workload (0/1: skip)")
     ap.add_argument("--cells", type=int, default=1_000_000)
