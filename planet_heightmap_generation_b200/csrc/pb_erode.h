@@ -63,8 +63,36 @@ struct AccumulateK {
         const int r = order[i];
         const int b = g.off[r], e = g.off[r + 1];
         float acc = initv ? initv[r] : 1.0f;
+        // donors that ran before this item, sorted by position — found BEFORE any polling (nothing here depends on other
+        // items), so that once the last donor's word arrives only the additions are left on the dependency chain
+        const int CAP = 12;
+        int dp[CAP], dd[CAP];
+        int n = 0;
+        bool fits = true;
+        for (int j = b; j < e; j++) {
+            const int d = g.adj[j];
+            const int p = pos[d];
+            if (target[d] != r || p < 0 || p >= i) continue;
+            if (n == CAP) { fits = false; break; }
+            int k = n++;
+            while (k > 0 && dp[k - 1] > p) { dp[k] = dp[k - 1]; dd[k] = dd[k - 1]; k--; }
+            dp[k] = p; dd[k] = d;
+        }
+        if (fits) {
+            unsigned long long w[CAP];
+            bool ok = false;
+            for (int s = 0; s < PB_SPIN && !ok; s++) {
+                ok = true;
+                for (int k = 0; k < n; k++) { w[k] = ld_word(contrib + dd[k]); }     // independent loads: one L2 round trip for all donors
+                for (int k = 0; k < n; k++) if (!word_seq(w[k])) ok = false;
+            }
+            if (!ok) return false;
+            for (int k = 0; k < n; k++) acc = (float)((double)acc + (double)word_value(w[k]));
+            st_word(contrib + r, make_word(acc, 1));
+            return true;
+        }
         int last = -1;
-        for (;;) {     // donors in position order (repeated-min: degree is tiny); each donor's word is polled directly
+        for (;;) {     // more donors than the local list holds: repeated-min over the row, each donor's word polled directly
             int bp = 0x7fffffff, bd = -1;
             for (int j = b; j < e; j++) {
                 const int d = g.adj[j];
@@ -184,23 +212,31 @@ struct SolveK {
         const int gg = tLand ? target[t] : -1;
         const bool gLand = gg >= 0 && !isOcean[gg] && gg != r;
         const int n0 = k0[r], n1 = tLand ? k1[r] : 0, n2 = gLand ? k2[r] : 0;
+        // everything that does not depend on other items is evaluated BEFORE the polling loop (the lane would only wait
+        // otherwise): the stream-power factor with its pow and divide, the static receiver / grand-receiver elevations
+        const float cd = cellDist[r];
+        const bool active = t >= 0 && cd > 0;
+        const double factor = active ? K * pb_pow((double)flow[r], m) * dt / (double)cd : 0.0;
+        const double htStatic = (active && !tLand) ? (double)elev[t] : 0.0;            // ocean receivers never change
+        const float cdt = (active && tLand && gg >= 0) ? cellDist[t] : 0.0f;
+        const double hgStatic = (active && tLand && gg >= 0 && !gLand && gg != r) ? (double)elev[gg] : 0.0;
         unsigned long long wr = 0, wt = 0, wg = 0;
         bool ok = false;
         for (int s = 0; s < PB_SPIN; s++) {
-            wr = ld_word(ec + r);
+            wr = ld_word(ec + r);                       // three independent loads per poll: one L2 round trip
+            if (tLand) wt = ld_word(ec + t);
+            if (gLand) wg = ld_word(ec + gg);
             if (word_seq(wr) != n0) continue;
-            if (tLand) { wt = ld_word(ec + t); if (word_seq(wt) != n1) continue; }
-            if (gLand) { wg = ld_word(ec + gg); if (word_seq(wg) != n2) continue; }
+            if (tLand && word_seq(wt) != n1) continue;
+            if (gLand && word_seq(wg) != n2) continue;
             ok = true;
             break;
         }
         if (!ok) return false;
-        const float cd = cellDist[r];
         float er = word_value(wr), et = tLand ? word_value(wt) : 0.0f;
-        if (t >= 0 && cd > 0) {
+        if (active) {
             const double hr0 = er;
-            const double ht = tLand ? (double)et : (double)elev[t];        // ocean receivers never change
-            const double factor = K * pb_pow((double)flow[r], m) * dt / (double)cd;
+            const double ht = tLand ? (double)et : htStatic;
             const double hrec = ht > 0 ? ht : 0.0;                 // Math.max(h_t, 0)
             double hnew = (hr0 + factor * hrec) / (1 + factor);
             if (hnew < hrec) hnew = hrec;
@@ -208,9 +244,9 @@ struct SolveK {
             const double eroded = hr0 - hnew;
             if (eroded > 0 && tLand) {
                 double slope = 0;
-                if (gg >= 0 && cellDist[t] > 0) {
-                    const double hg = gLand ? (double)word_value(wg) : (gg == r ? hr0 : (double)elev[gg]);
-                    slope = fabs(ht - hg) / (double)cellDist[t];
+                if (gg >= 0 && cdt > 0) {
+                    const double hg = gLand ? (double)word_value(wg) : (gg == r ? hr0 : hgStatic);
+                    slope = fabs(ht - hg) / (double)cdt;
                 }
                 const double deposit = eroded * (0.5 / (1 + slope * 50));
                 float nt = (float)(ht + deposit);
