@@ -273,32 +273,47 @@ struct Mesh {
         if (src != elev) dev_copy(elev, src, sizeof(float) * (size_t)N, 2, ex().stream);
     }
 
-    // pass 1 on one host core (the default, pb_flood.h): elev / key0 / drainTo / visited / seeds come down over PCIe
-    // into pinned buffers (13 B/cell), surface and drainTo go back up (8 B/cell)
-    PinnedBuf<float> hfElev, hfSurface, hfKey0;
-    PinnedBuf<int> hfDrain, hfSeeds;
-    PinnedBuf<uint8_t> hfVisited;
+    // pass 1 on one host core (the default, pb_flood.h): (elevation, key) pairs, the visited bitmap, drainTo and the
+    // seed list come down over PCIe into pinned buffers (≈ 12 B/cell), drainTo and the sparse list of filled cells go back up
+    PinnedBuf<FloodEK> hfEK;
+    PinnedBuf<int> hfDrain, hfSeeds, hfFilledCell;
+    PinnedBuf<float> hfFilledSurf;
+    PinnedBuf<uint32_t> hfBits;
+    DevBuf<FloodEK> dEK;
+    DevBuf<uint32_t> dBits;
+    DevBuf<int> dFilledCell;
+    DevBuf<float> dFilledSurf;
     std::vector<HostHeapEntry> hfHeap;
+    std::vector<float> hfSurf, hfFS;
+    std::vector<int> hfFC;
     double lastFloodHostMs = 0;
     void flood_heap_on_host(const float* elev) {
         const Exec& x = ex();
-        hfElev.ensure(N); hfSurface.ensure(N); hfKey0.ensure(N); hfDrain.ensure(N); hfVisited.ensure(N); hfSeeds.ensure(N);
+        const int words = (N + 31) / 32;
+        x.for_each(words, FloodBitmapK{visited.p, N, dBits.ensure(words)});
+        x.for_each(N, FloodPackK{elev, key.p, dEK.ensure(N)});
+        hfEK.ensure(N); hfDrain.ensure(N); hfSeeds.ensure(N); hfBits.ensure(words);
         int nSeeds = 0;
         dev_copy(&nSeeds, counters.p + 0, sizeof(int), 1, x.stream);
-        dev_copy(hfElev.data(), elev, sizeof(float) * (size_t)N, 1, x.stream);
-        dev_copy(hfKey0.data(), key.p, sizeof(float) * (size_t)N, 1, x.stream);
+        dev_copy(hfEK.data(), dEK.p, sizeof(FloodEK) * (size_t)N, 1, x.stream);
         dev_copy(hfDrain.data(), drainTo.p, sizeof(int) * (size_t)N, 1, x.stream);
-        dev_copy(hfVisited.data(), visited.p, (size_t)N, 1, x.stream);
+        dev_copy(hfBits.data(), dBits.p, sizeof(uint32_t) * (size_t)words, 1, x.stream);
         dev_copy(hfSeeds.data(), seeds.p, sizeof(int) * (size_t)N, 1, x.stream);   // nSeeds is not known yet: the list is ≤ N ints
         stream_sync(x.stream);
-        memcpy(hfSurface.data(), hfElev.data(), sizeof(float) * (size_t)N);         // surface starts as a copy of the elevation (:107)
         const auto t0 = std::chrono::steady_clock::now();
-        flood_heap_host(N, hOffCopy.data(), hAdjCopy.data(), hfElev.data(), hfSurface.data(), hfKey0.data(), hfDrain.data(),
-                        hfVisited.data(), hfSeeds.data(), nSeeds, hfHeap);
+        flood_heap_host(N, hOffCopy.data(), hAdjCopy.data(), hfEK.data(), nullptr, hfDrain.data(), hfBits.data(), hfSeeds.data(), nSeeds,
+                        hfHeap, hfSurf, hfFC, hfFS);
         lastFloodHostMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (getenv("PB_DEBUG")) fprintf(stderr, "[pb] flood pass 1 on the host: %d seeds, %.2f ms\n", nSeeds, lastFloodHostMs);
-        dev_copy(surface.p, hfSurface.data(), sizeof(float) * (size_t)N, 0, x.stream);
+        if (getenv("PB_DEBUG")) fprintf(stderr, "[pb] flood pass 1 on the host: %d seeds, %zu filled cells, %.2f ms\n", nSeeds, hfFC.size(), lastFloodHostMs);
+        const size_t nf = hfFC.size();
         dev_copy(drainTo.p, hfDrain.data(), sizeof(int) * (size_t)N, 0, x.stream);
+        if (nf) {
+            memcpy(hfFilledCell.ensure(nf), hfFC.data(), sizeof(int) * nf);
+            memcpy(hfFilledSurf.ensure(nf), hfFS.data(), sizeof(float) * nf);
+            dev_copy(dFilledCell.ensure(nf), hfFilledCell.data(), sizeof(int) * nf, 0, x.stream);
+            dev_copy(dFilledSurf.ensure(nf), hfFilledSurf.data(), sizeof(float) * nf, 0, x.stream);
+            x.for_each((int)nf, FloodFilledK{dFilledCell.p, dFilledSurf.p, surface.p});     // surface was initialised to the elevation by FloodInitK
+        }
         stream_sync(x.stream);
     }
 #if PB_CUDA
@@ -351,7 +366,7 @@ struct Mesh {
                         liftUp.p, levels, N, dIn, carveStrength};
         launch_stats().launches++;
         ProfScope ps(x.prof, "pb::k_carve_lift", x.stream);
-        k_carve_lift<<<nSeg, PB_CARVE_THREADS, 0, x.stream>>>(a);
+        k_carve_lift<<<(nSeg + PB_CARVE_WARPS - 1) / PB_CARVE_WARPS, PB_CARVE_THREADS, 0, x.stream>>>(a);
         PB_CUDA_CHECK(cudaGetLastError());
     }
 #endif
