@@ -474,6 +474,94 @@ def pipelined_throughput(args, mesh, xyz, local, planets: int, steps: int):
 
 
 # ---------------------------------------------------------------------------------------------------
+# cell-range sharded sweep loops: strong scaling of ONE planet's climate stack across the ranks
+# ---------------------------------------------------------------------------------------------------
+def build_eroded_planet(dm, cells, hiters):
+    """(elev, pio, r_plate) of the seeded planet on `dm`: plates → assignElevation → runPostProcessing, all on the device"""
+    import torch
+    from planet_heightmap_generation_b200 import plates as pl
+    from planet_heightmap_generation_b200.elevation import assignElevation
+    from planet_heightmap_generation_b200.terrain_post import runPostProcessing
+    dev = torch.device("cuda", torch.cuda.current_device())
+    N = cells + 1
+    r_plate = torch.empty(N, dtype=torch.int32, device=dev)
+    r_super = torch.empty(N, dtype=torch.int32, device=dev)
+    cp = pl.generateCoarsePlates(dm, SEED, NUM_PLATES, NUM_CONTINENTS, SIZE_VARIETY, LAND_COVERAGE, N_COARSE)
+    seeds, vec, pio, dens = cp["coarsePlateSeeds"], cp["coarsePlateVec"], cp["coarsePlateIsOcean"], cp["plateDensity"]
+    pl.projectCoarsePlates(dm, None, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], SEED, NUM_PLATES, out=r_plate)
+    cp["coarseMesh"].close()
+    pl.smoothAndReconnectPlates(dm, r_plate, seeds, 3)
+    sp = pl.buildSuperPlates(dm, r_plate, seeds, vec, pio, dens, out=r_super)
+    res = assignElevation(dm, None, pio, r_plate, vec, seeds, SEED, NMAG, SEED, SPREAD, dens, sp)
+    elev = res["r_elevation"]
+    runPostProcessing(dm, None, elev, SLIDERS, None, SEED, res["debugLayers"]["hotspot"], hItersOverride=hiters, timing=False)
+    return elev, pio, r_plate
+
+
+def sharded_climate_probe(args, rank, world, local, cells, steps=2):
+    """Supplementary line of an N-GPU run in replicas mode: the climate stack of ONE `cells`-cell planet (BASELINE config 4
+    size by default) with its sweep loops sharded by cell-id range over the N ranks, against the same stack unsharded on one
+    GPU, results compared bit for bit.  Every rank holds the planet (replicated), so no rank is idle in either run."""
+    import torch
+    import torch.distributed as dist
+    from planet_heightmap_generation_b200 import climate as cl
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    from planet_heightmap_generation_b200.sharded import SweepShardGroup
+    dev = torch.device("cuda", local)
+    t_setup = time.perf_counter()
+    dm = DeviceMesh.build_sphere(cells, 0.75, SEED, device=local)
+    N = cells + 1
+    group = SweepShardGroup(dm, rank, world, min_cells=0)
+    group.set_min_cells(1 << 62)                       # the planet itself is built unsharded
+    elev, pio, r_plate = build_eroded_planet(dm, cells, 10)
+    koppen = torch.empty(N, dtype=torch.uint8, device=dev)
+    setup_s = time.perf_counter() - t_setup
+
+    def run(k):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = cl.computeClimate(dm, elev, pio, r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k, out
+
+    run(1)
+    ms_one, out = run(steps)
+    st = cl._state(dm)
+    keys = ("r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter", "r_ocean_warmth_summer")
+    ref = {k: torch.from_numpy(st.field(k)) for k in keys}
+    ref_koppen = koppen.clone()
+    group.set_min_cells(0)
+    before = group.info()
+    run(1)
+    ms_sh, out = run(steps)
+    info = group.info()
+    same = bool((koppen == ref_koppen).all().item()) and all(bool((torch.from_numpy(st.field(k)) == ref[k]).all().item()) for k in keys)
+    flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    group.close()
+    dm.close()
+    sweeps = (info["sweeps_sharded"] - before["sweeps_sharded"]) // (steps + 1)
+    return {"what": f"climate stack of one {N}-cell planet (820 → {sweeps} graph sweeps per pass at this size), sweep loops sharded by "
+                    f"contiguous cell-id range over {world} GPUs with a one-cell halo pushed into peer memory by the sweep kernels "
+                    f"(CUDA IPC over NVLink), ranges all-gathered at the end of every loop; everything else replicated",
+            "cells": N, "n_gpus": world, "ms_per_pass_unsharded_1gpu": ms_one, "ms_per_pass_sharded": ms_sh,
+            "speedup": ms_one / ms_sh, "cells_per_s_sharded": N / (ms_sh / 1e3), "sweeps_per_pass": int(sweeps),
+            "loops_per_pass": int((info["loops_sharded"] - before["loops_sharded"]) // (steps + 1)),
+            "halo_bytes_per_sweep_rank0": info["halo_bytes_per_sweep"], "adjacent_ranks_rank0": info["adjacent_ranks"],
+            "rows_rank0": info["hi"] - info["lo"], "bit_identical_to_unsharded_on_every_rank": bool(flag.item()),
+            "setup_s": setup_s,
+            "limiter": "the replicated part of the stack (pointwise kernels, 5 BFS, 6 radix sorts for the percentiles, ITCZ bins) "
+                       "does not shrink with N; the sharded sweeps are bounded by the per-sweep flag round trip over NVLink"}
+
+
+
+# ---------------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -506,6 +594,12 @@ def run_b200(args):
     mesh, xyz = inp.mesh, inp.xyz
     N, E = mesh.numRegions, int(mesh.adjList.shape[0])
     dm = DeviceMesh(mesh, xyz, device=local)
+    shards_mode = world > 1 and args.multi_gpu == "shards"
+    group = None
+    if shards_mode:
+        from planet_heightmap_generation_b200.sharded import SweepShardGroup
+        group = SweepShardGroup(dm, rank, world, min_cells=None if args.shard_min_cells < 0 else args.shard_min_cells)
+    planets = 1 if shards_mode else world          # strong scaling: every rank works on the same planet
     xyz_t = torch.empty(3 * N, dtype=torch.float32, device=dev)
     off_t = torch.empty(N + 1, dtype=torch.int32, device=dev)
     adj_t = torch.empty(E, dtype=torch.int32, device=dev)
@@ -615,7 +709,7 @@ def run_b200(args):
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
-    value = N * world * args.steps / (ms_total / 1000.0)
+    value = N * planets * args.steps / (ms_total / 1000.0)
 
     # ---- end to end through the host-pointer C ABI ------------------------------------------------
     elev_dev_final = state["elev"].clone()
@@ -693,7 +787,7 @@ def run_b200(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = N * world * args.steps / e2e_s
+    e2e_value = N * planets * args.steps / e2e_s
     # host-pointer and device-pointer passes agree bit for bit
     if do_plates:
         mesh_same = mesh_same and bool((h_plate == r_plate_dev_final.cpu()).all().item()) and bool((h_super == r_super_dev_final.cpu()).all().item())
@@ -777,7 +871,7 @@ def run_b200(args):
 
     # ---- several planets in flight (supplementary: `value` above is one planet at a time) ----------------------
     in_flight = None
-    if wl == "full" and args.in_flight > 1:
+    if wl == "full" and args.in_flight > 1 and not shards_mode:
         secs, agree, ref = pipelined_throughput(args, mesh, xyz, local, args.in_flight, args.steps)
         if world > 1:
             t = torch.tensor([secs], dtype=torch.float64, device=dev)
@@ -789,17 +883,43 @@ def run_b200(args):
                      "note": "one pb_context + CUDA stream + host thread per planet, same full pipeline per planet; host wall clock "
                              "around device synchronizes"}
 
+    # ---- the data path that shards: sweep loops by cell-id range (pb_shardsweep.h) -------------------------------
+    sharding = None
+    if shards_mode:
+        info = group.info()
+        # the same climate pass unsharded on this GPU must give the same bits
+        ident = None
+        if do_clim:
+            ref_k = koppen.clone()
+            group.set_min_cells(1 << 62)
+            cl.computeClimate(dm, state["elev"], state["pio"], r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
+            torch.cuda.synchronize()
+            ok = torch.tensor([1 if bool((koppen == ref_k).all().item()) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            ident = bool(ok.item())
+        sharding = {"rows_rank0": info["hi"] - info["lo"], "adjacent_ranks_rank0": info["adjacent_ranks"],
+                    "halo_bytes_per_sweep_rank0": info["halo_bytes_per_sweep"], "sharded_sweeps_total_rank0": info["sweeps_sharded"],
+                    "sharded_loops_total_rank0": info["loops_sharded"], "loops_sharded": info["active"], "min_cells": info["min_cells"],
+                    "koppen_bit_identical_to_unsharded_on_every_rank": ident,
+                    "limiter": "Amdahl: the class S/R stages (host-serial heap flood and randomized fills, dependency-latency-bound "
+                               "solve / accumulate, stable sort) and the pointwise / BFS / sort kernels run replicated on every rank; "
+                               "only the Jacobi / propagation sweep loops shrink with N"}
+        dist.barrier()
+        group.close()
+    elif world > 1 and args.shard_probe_cells > 0 and wl == "full":
+        sharding = sharded_climate_probe(args, rank, world, local, args.shard_probe_cells)
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if shards_mode else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "impl": "b200", "config": bench_config(args, world), "land_cells": land, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
                     "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
-            "cpu_baseline": cpu_baseline, "throughput_in_flight": in_flight, "kernel_breakdown": breakdown, "library": dm.lib.version,
+            "cpu_baseline": cpu_baseline, "sharded_sweeps": sharding, "throughput_in_flight": in_flight, "kernel_breakdown": breakdown, "library": dm.lib.version,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -811,13 +931,14 @@ def run_b200(args):
 # sharded sweeps: the one data path that has a real exchange step (cell-range shards + one-cell halo per sweep)
 # ---------------------------------------------------------------------------------------------------
 def run_sharded_sweeps(args):
-    """`--workload sharded-sweeps`: smoothField (js/climate-util.js:5-25) over a mesh sharded by contiguous cell-id
-    ranges across the ranks, one halo exchange (torch.distributed p2p over NCCL) per sweep.  Strong scaling of one
-    planet: value = cells × sweeps per second."""
+    """`--workload sharded-sweeps`: smoothField (js/climate-util.js:5-25) on a planet whose sweep loops are sharded by
+    contiguous cell-id ranges across the ranks (csrc/pb_shardsweep.h: halo values stored into peer memory by the sweep
+    kernel, all-gather at the end of the loop).  Strong scaling of one planet: value = cells × sweeps per second."""
     import torch
     import torch.distributed as dist
+    from planet_heightmap_generation_b200.climate_util import smoothField
     from planet_heightmap_generation_b200.engine import DeviceMesh
-    from planet_heightmap_generation_b200.sharded import HaloExchanger, PeerHaloSmoother, Shard, smoothFieldSharded
+    from planet_heightmap_generation_b200.sharded import SweepShardGroup
     from planet_heightmap_generation_b200.sphere import synthetic_elevation
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -827,26 +948,16 @@ def run_sharded_sweeps(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    mesh, xyz = get_planet(args.cells, on_device=local)
-    N = mesh.numRegions
-    field0 = synthetic_elevation(xyz, SEED, 0.3)
-    sh = Shard(mesh, xyz, world, rank)
-    dm = DeviceMesh(sh.mesh, sh.r_xyz, device=local)
-    ex = HaloExchanger(sh, dev) if (world > 1 and args.halo == "nccl") else None
-    peer = PeerHaloSmoother(dm, sh) if (world > 1 and args.halo == "peer") else None
-    f0 = torch.from_numpy(sh.scatter(field0)).to(dev)
+    dm = DeviceMesh.build_sphere(args.cells, 0.75, SEED, device=local)
+    N = args.cells + 1
+    f0 = torch.from_numpy(synthetic_elevation(dm.r_xyz, SEED, 0.3)).to(dev)
+    group = SweepShardGroup(dm, rank, world, min_cells=0) if world > 1 else None
     f = f0.clone()
     sweeps = args.sweeps
-    from planet_heightmap_generation_b200.climate_util import smoothField
 
     def step():
         f.copy_(f0)
-        if peer is not None:
-            peer.smooth(f, sweeps)            # halo values stored into peer memory by the kernels, flags over NVLink
-        elif ex is not None:
-            smoothFieldSharded(dm, ex, f, sweeps)   # one torch.distributed p2p exchange per sweep
-        else:
-            smoothField(dm, f, sweeps)
+        smoothField(dm, f, sweeps)
 
     def barrier():
         torch.cuda.synchronize()
@@ -868,23 +979,20 @@ def run_sharded_sweeps(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    info = group.info() if group else None
     if rank == 0:
         per_sweep_us = 1000 * ms / (args.steps * sweeps)
         print(json.dumps({
             "metric": "cell_sweeps_per_sec_sharded_smoothField", "value": N * sweeps * args.steps / (ms / 1000), "unit": "cell-sweeps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{N}-cell sphere, {sweeps} smoothField sweeps per step, cell-range shards, one-cell halo "
-                                   f"exchange per sweep" + ("" if world == 1 else
-                                   " by peer-memory stores + flags (CUDA IPC over NVLink)" if peer is not None else " over NCCL p2p"),
-                       "halo": "none" if world == 1 else args.halo, "us_per_sweep": per_sweep_us,
-                       "halo_cells_rank0": int(sh.halo.size), "halo_bytes_per_sweep_rank0": sh.halo_bytes_per_sweep,
-                       "peers_rank0": sorted(sh.recv)},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "b200",
+            "config": {"workload": f"{N}-cell sphere, {sweeps} smoothField sweeps per step, cell-range shards, one-cell halo pushed into "
+                                   f"peer memory by the sweep kernel (CUDA IPC over NVLink), all-gather at the end of the loop",
+                       "us_per_sweep": per_sweep_us, "shards": info},
             "algorithmic_GBps": 36.0 * N / (per_sweep_us * 1e-6) / 1e9}), flush=True)
-    if peer is not None:
-        torch.cuda.synchronize()
-        dist.barrier()
-        peer.close()
+    if group:
+        barrier()
+        group.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -901,11 +1009,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="full", choices=["full", "post", "climate", "elevation", "elevation+post", "mesh", "plates", "sharded-sweeps"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step of --workload sharded-sweeps")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="halo exchange of --workload sharded-sweeps")
     ap.add_argument("--flood", default="", choices=["", "device", "host"],
                     help="engine option: where the serial heap pass of priorityFloodCarve runs (default host)")
-    ap.add_argument("--multi-gpu", default="replicas", choices=["replicas", "shards"], dest="multi_gpu",
-                    help="N>1: independent planets per GPU (weak) or one planet with cell-range sharded sweep loops (strong)")
+    ap.add_argument("--multi-gpu", default="auto", choices=["auto", "replicas", "shards"], dest="multi_gpu",
+                    help="N>1: independent planets per GPU (weak) or ONE planet whose sweep loops are sharded by cell-id range "
+                         "(strong); auto = shards from 4M cells up (below that a sweep is shorter than the halo flag round trip)")
+    ap.add_argument("--shard-min-cells", type=int, default=-1, dest="shard_min_cells",
+                    help="engine threshold below which sweep loops stay unsharded (-1: engine default, 0: always shard)")
+    ap.add_argument("--shard-probe-cells", type=int, default=10_000_000, dest="shard_probe_cells",
+                    help="N>1, replicas mode: size of the supplementary sharded climate measurement (0: skip)")
     ap.add_argument("--in-flight", type=int, default=4, dest="in_flight",
                     help="planets kept in flight per GPU for the supplementary throughput figure of the full workload (0/1: skip)")
     ap.add_argument("--cells", type=int, default=1_000_000)
@@ -914,6 +1026,8 @@ def main():
                                                    "(default: the kernel with the largest device time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.multi_gpu == "auto":
+        args.multi_gpu = "shards" if args.cells >= 4_000_000 else "replicas"
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: fewer than 3 warm-up steps requested")
     if args.workload == "sharded-sweeps":

@@ -309,23 +309,27 @@ pb_status pb_mesh_get_adj_triangles(pb_mesh* mesh, int32_t* adjTriList);
 pb_status pb_generate_triangle_centers(pb_mesh* mesh, float* t_xyz);
 pb_status pb_compute_triangle_elevations(pb_mesh* mesh, const float* r_elevation, float* t_elevation);
 
-/* ---- cell-range shards with device-side halo exchange (no reference counterpart: the reference is one thread) ----
- * One process per GPU.  `mesh` is the rank's LOCAL mesh: owned cells [0, nOwn) followed by the halo cells its rows
- * read (halo rows empty), see planet_heightmap_generation_b200/sharded.py.  For every peer the caller gives the
- * owned cells that peer reads (send list, local ids) and the offset at which this rank's block starts inside the
- * peer's local field.  The shard's buffers are exported as CUDA IPC handles (4 x 64 bytes) and the peers' handles
- * are connected once; afterwards pb_smooth_field_sharded runs `passes` smoothField sweeps (js/climate-util.js:5-25)
- * in which every rank's kernels store their boundary values straight into the peers' halo slots over NVLink and
- * synchronise through flags in peer memory — no NCCL call and no host round trip per sweep.  Results are
- * bit-identical to pb_smooth_field on the unsharded mesh.  Device pointers only (PB_POINTER_DEVICE). */
-typedef struct pb_shard pb_shard;
-pb_status pb_shard_create(pb_mesh* mesh, int32_t nOwn, int32_t myRank, int32_t worldSize, int32_t nPeers,
-                          const int32_t* peerRanks, const int32_t* sendCounts, const int32_t* sendIdx,
-                          const int32_t* peerRecvOffset, pb_shard** out);
-void pb_shard_destroy(pb_shard* shard);
-pb_status pb_shard_export(pb_shard* shard, unsigned char* handles256);
-pb_status pb_shard_connect(pb_shard* shard, int32_t peerIndex, const unsigned char* handles256);
-pb_status pb_smooth_field_sharded(pb_shard* shard, float* field, int32_t passes);
+/* ---- cell-range shards of the sweep loops (no reference counterpart: the reference is one thread) ----
+ * One process per GPU; every rank creates the SAME mesh (the whole planet) and attaches a shard group to it.  From then
+ * on every Jacobi / propagation sweep loop run on that mesh — pb_smooth_field (js/climate-util.js:5-25) and the loops
+ * inside pb_compute_ocean_currents / pb_compute_precipitation / pb_compute_temperature / pb_compute_wind (smoothOcean
+ * js/ocean.js:168-189, advectMoisture js/precipitation.js:118-179, rain-shadow / windward propagation :555-598,
+ * diffuseOceanWarmth js/temperature.js:33-51) — computes only the rows of this rank's contiguous cell-id range
+ * [N*rank/world, N*(rank+1)/world) and exchanges the one-cell halo with the adjacent ranges by storing the boundary
+ * values straight into the peers' buffers over NVLink (CUDA-IPC mapped memory, flags in peer memory; no NCCL call and
+ * no host round trip per sweep); at the end of a loop the ranges are all-gathered by peer stores so that the field is
+ * whole on every rank again.  Everything else of the pipeline runs replicated.  Results are bit-identical to the
+ * unsharded calls.  Planets below `minCells` (default 2 000 000) keep running unsharded: one sweep is then shorter than
+ * the flag round trip.  Handles: 3 x 64 bytes (two sweep buffers, one control block), exchanged once by the caller
+ * (torch.distributed all_gather in the Python mirror).  All ranks must issue the same sequence of calls. */
+typedef struct pb_sweep_shards pb_sweep_shards;
+pb_status pb_sweep_shards_create(pb_mesh* mesh, int32_t rank, int32_t worldSize, pb_sweep_shards** out);
+void pb_sweep_shards_destroy(pb_sweep_shards* shards);
+pb_status pb_sweep_shards_export(pb_sweep_shards* shards, unsigned char* handles192);
+pb_status pb_sweep_shards_connect(pb_sweep_shards* shards, int32_t peerRank, const unsigned char* handles192);
+pb_status pb_sweep_shards_set_min_cells(pb_sweep_shards* shards, int64_t minCells);
+/* out8: first row, end row, adjacent ranks, halo bytes sent per sweep, sweeps run sharded, loops run sharded, active, minCells */
+pb_status pb_sweep_shards_info(pb_sweep_shards* shards, int64_t* out8);
 
 #ifdef __cplusplus
 }

@@ -83,11 +83,12 @@ SYMBOLS = {
     "pb_triangulate_sphere": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "pb_mesh_create_from_points": (C.c_int, [_vp, _i32, _vp, C.POINTER(_vp)]),
     "pb_mesh_get_adjacency": (C.c_int, [_vp, _vp, _vp]),
-    "pb_shard_create": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
-    "pb_shard_destroy": (None, [_vp]),
-    "pb_shard_export": (C.c_int, [_vp, _vp]),
-    "pb_shard_connect": (C.c_int, [_vp, _i32, _vp]),
-    "pb_smooth_field_sharded": (C.c_int, [_vp, _vp, _i32]),
+    "pb_sweep_shards_create": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "pb_sweep_shards_destroy": (None, [_vp]),
+    "pb_sweep_shards_export": (C.c_int, [_vp, _vp]),
+    "pb_sweep_shards_connect": (C.c_int, [_vp, _i32, _vp]),
+    "pb_sweep_shards_set_min_cells": (C.c_int, [_vp, _i64]),
+    "pb_sweep_shards_info": (C.c_int, [_vp, _vp]),
 }
 
 

@@ -5,6 +5,7 @@
 // resident in HBM under their reference key names; callers read individual fields back by name.
 #pragma once
 #include "pb_engine.h"
+#include "pb_shardsweep.h"
 #include "pb_climate.h"
 
 namespace pb {
@@ -44,13 +45,8 @@ struct Climate {
 
     // ---- shared building blocks -------------------------------------------------------------------------
     void smooth_masked(float* field, const uint8_t* mask, int passes, bool zeroOutside) {
-        if (passes <= 0) return;
-        float* src = field; float* dst = m->tmp.ensure(N);
-        for (int p = 0; p < passes; p++) {
-            if (!m->sweep_tiled(1, src, dst, mask, nullptr, zeroOutside)) ex().for_each(N, SmoothMaskedK{csr(), mask, src, dst, zeroOutside ? 1 : 0});
-            std::swap(src, dst);
-        }
-        if (src != field) dev_copy(field, src, sizeof(float) * (size_t)N, 2, ex().stream);
+        const Csr g = csr(); const int z = zeroOutside ? 1 : 0;
+        sweep_loop(*m, field, passes, m->tmp.ensure(N), [=](const float* src, float* dst) { return SmoothMaskedK{g, mask, src, dst, z}; });
     }
 
     // hop counts from the cells flagged in seedFlag (their dist is already 0, everything else -1)
@@ -278,11 +274,13 @@ struct Climate {
             x.for_each(N, ConvergenceK{g, m->xyz.p, wX, wY, wZ, conv});
             m->smooth_field(conv, convSmoothPasses);
             // advectMoisture (:59-182)
-            float* src = bufA; float* dst = bufB;
+            float* src = bufA;
             x.for_each(N, MoistureInitK{g, m->xyz.p, isLand, coastDistLand, cF("r_ocean_warmth_" + name), wX, wY, wZ, src});
-            for (int it = 0; it < maxHops; it++) {
-                x.for_each(N, AdvectK{g, m->xyz.p, isLand, windE, windN, wX, wY, wZ, heightKm, src, dst, depletionBase, maxHops});
-                std::swap(src, dst);
+            {
+                const float* xyzp = m->xyz.p;
+                sweep_loop(*m, src, maxHops, bufB, [=](const float* in, float* out) {
+                    return AdvectK{g, xyzp, isLand, windE, windN, wX, wY, wZ, heightKm, in, out, depletionBase, maxHops};
+                });
             }
             float* precip = F("r_precip_complex_" + name);
             float* rainShadow = F("r_rainshadow_" + name);
@@ -296,16 +294,16 @@ struct Climate {
             dev_copy(shadowField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
             dev_copy(windwardField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
             {
-                float* a = ping; float* b = pong;
-                dev_copy(a, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                for (int it = 0; it < shadowHops; it++) { x.for_each(N, ShadowSweepK{g, isLand, upWt.p, a, b, 1 - shadowDecay, -1}); std::swap(a, b); }
-                x.for_each(N, KeepExtremeK{a, shadowField, -1});
+                const float* wt = upWt.p; const double keep = 1 - shadowDecay;
+                dev_copy(ping, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
+                sweep_loop(*m, ping, shadowHops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, -1}; });
+                x.for_each(N, KeepExtremeK{ping, shadowField, -1});
             }
             {
-                float* a = ping; float* b = pong;
-                dev_copy(a, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                for (int it = 0; it < windwardHops; it++) { x.for_each(N, ShadowSweepK{g, isLand, dnWt.p, a, b, 1 - windwardDecay, +1}); std::swap(a, b); }
-                x.for_each(N, KeepExtremeK{a, windwardField, +1});
+                const float* wt = dnWt.p; const double keep = 1 - windwardDecay;
+                dev_copy(ping, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
+                sweep_loop(*m, ping, windwardHops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, +1}; });
+                x.for_each(N, KeepExtremeK{ping, windwardField, +1});
             }
             x.for_each(N, MergeShadowK{shadowField, windwardField, rainShadow});
             m->smooth_field(rainShadow, rsSmoothPasses);
@@ -341,12 +339,9 @@ struct Climate {
         for (int s = 0; s < 2; s++) {
             const std::string name = s == 0 ? "summer" : "winter";
             const float* warmth = cF("r_ocean_warmth_" + name);
-            float* src = a0.ensure(N); float* dst = a1.ensure(N);
+            float* src = a0.ensure(N);
             x.for_each(N, CoastalSeedK{cU("r_isLand"), warmth, src});
-            for (int p = 0; p < passes; p++) {
-                if (!m->sweep_tiled(2, src, dst, nullptr, pcont, false)) x.for_each(N, DiffuseWarmthK{g, pcont, src, dst});
-                std::swap(src, dst);
-            }
+            sweep_loop(*m, src, passes, a1.ensure(N), [=](const float* in, float* out) { return DiffuseWarmthK{g, pcont, in, out}; });
             float* temp = F("r_temperature_" + name);
             x.for_each(N, TemperatureK{cF("r_lat"), cF("r_lon"), cU("r_isLand"), elev, cF("r_continentality"), pcont,
                                        cF(s == 0 ? "itczLatsSummer" : "itczLatsWinter"), warmth, cF("r_ocean_speed_" + name),

@@ -10,7 +10,6 @@
 #include "pb_prims.h"
 #include "pb_flood.h"
 #include "pb_erode.h"
-#include "pb_tiled.h"
 #include "../../include/planet_b200.h"
 
 namespace pb {
@@ -78,8 +77,15 @@ struct StageTimer {
     }
 };
 
+struct SweepShards;
+struct Mesh;
+// `passes` double-buffered sweeps field ← F(field): on this GPU alone, or — when a shard group is attached to the mesh and
+// the planet is large enough — over this rank's cell-id range with a peer-memory halo exchange per sweep (pb_shardsweep.h)
+void smooth_field_impl(Mesh& m, float* field, int passes);
+
 struct Mesh {
     Context* ctx;
+    SweepShards* shards = nullptr;      // set by pb_mesh_attach_shards (not owned)
     int N = 0;
     long long E = 0;
     DevBuf<int> off, adj;
@@ -119,7 +125,6 @@ struct Mesh {
         E = hOff[n];
         for (long long i = 0; i < E; i++) if (hAdj[i] < 0 || hAdj[i] >= n) throw Error("adjList entry out of range");
         hOffCopy.assign(hOff, hOff + n + 1); hAdjCopy.assign(hAdj, hAdj + E); hXyzCopy.assign(hXyz, hXyz + 3 * (size_t)n);
-        compute_tile_geometry(hOff, hAdj);
         const Exec& ex = ctx->ex;
         dev_copy(off.ensure(n + 1), hOff, sizeof(int) * (size_t)(n + 1), 0, ex.stream);
         dev_copy(adj.ensure(E), hAdj, sizeof(int) * (size_t)E, 0, ex.stream);
@@ -127,63 +132,6 @@ struct Mesh {
         ndist.ensure(E);
         ex.for_each(N, NeighborDistK{csr(), xyz.p, ndist.p});
         stream_sync(ex.stream);
-    }
-
-    // ---- tiled sweeps (pb_tiled.h): window half-width that covers 99.9 % of the edges, shared-memory budget ----
-    int tileW = 0, tileAdjCap = 0, tileSmem = 0;
-    bool tiledOk = false;
-    void compute_tile_geometry(const int* hOff, const int* hAdj) {
-#if PB_CUDA
-        // Measured on B200 at 1M cells (profiles/r01_sweeps_ncu.md): the staged variant is SLOWER than the plain gather kernel
-        // (27 µs vs 17 µs per smoothField sweep) because the id window is wide (W ≈ 4 200 ids for a 1 024-cell tile → 2× the
-        // L2→SM traffic, two CTAs per SM, no load/compute overlap).  It stays opt-in (PB_TILED=1) until cells are renumbered
-        // for locality.
-        if (N < 4 * 1024 || !getenv("PB_TILED")) return;
-        // histogram of |nb - r| in steps of 64 ids
-        const int STEP = 64;
-        std::vector<long long> hist((size_t)N / STEP + 2, 0);
-        for (int r = 0; r < N; r++)
-            for (int j = hOff[r]; j < hOff[r + 1]; j++) { const int d = hAdj[j] > r ? hAdj[j] - r : r - hAdj[j]; hist[d / STEP]++; }
-        long long acc = 0; const long long want = (long long)((double)E * 0.999);
-        int W = 0;
-        for (size_t k = 0; k < hist.size(); k++) { acc += hist[k]; if (acc >= want) { W = (int)(k + 1) * STEP; break; } }
-        W = (W + 3) & ~3;
-        int maxAdj = 0;
-        for (int r0 = 0; r0 < N; r0 += 1024) { const int r1 = std::min(N, r0 + 1024); maxAdj = std::max(maxAdj, hOff[r1] - (hOff[r0] & ~3)); }
-        const int adjCap = (maxAdj + 7) & ~3;
-        const size_t smem = 16 + sizeof(float) * (size_t)(1024 + 2 * W + 8) + sizeof(int) * (size_t)(1024 + 4) + sizeof(int) * (size_t)(adjCap + 8);
-        int dev = 0, lim = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (smem + 1024 > (size_t)lim / 2) return;            // keep two CTAs per SM; larger windows use the plain kernels
-        tileW = W; tileAdjCap = adjCap; tileSmem = (int)smem; tiledOk = true;
-        PB_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tileSmem));
-        PB_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tileSmem));
-        PB_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tileSmem));
-        if (getenv("PB_DEBUG")) fprintf(stderr, "[pb] tiled sweeps: W = %d ids, adjCap = %d, %d bytes of shared memory per CTA\n", W, adjCap, tileSmem);
-#else
-        (void)hOff; (void)hAdj;
-#endif
-    }
-    // one sweep dst = op(src); returns false when the tiled path does not apply (caller uses the plain kernel)
-    bool sweep_tiled(int mode, const float* src, float* dst, const uint8_t* mask, const float* pcont, bool zeroOutside) {
-#if PB_CUDA
-        if (!tiledOk || ((uintptr_t)src & 15)) return false;
-        const Exec& x = ex();
-        const int grid = (N + 1023) / 1024;
-        const TileGeom tg{tileW, tileAdjCap};
-        launch_stats().launches++;
-        static const char* names[3] = {"pb::k_sweep_tiled<smoothField>", "pb::k_sweep_tiled<masked>", "pb::k_sweep_tiled<diffuseWarmth>"};
-        ProfScope ps(x.prof, names[mode], x.stream);
-        if (mode == 0) k_sweep_tiled<0><<<grid, PB_TILE_THREADS, tileSmem, x.stream>>>(csr(), src, dst, mask, pcont, 0, tg);
-        else if (mode == 1) k_sweep_tiled<1><<<grid, PB_TILE_THREADS, tileSmem, x.stream>>>(csr(), src, dst, mask, pcont, zeroOutside ? 1 : 0, tg);
-        else k_sweep_tiled<2><<<grid, PB_TILE_THREADS, tileSmem, x.stream>>>(csr(), src, dst, mask, pcont, 0, tg);
-        PB_CUDA_CHECK(cudaGetLastError());
-        return true;
-#else
-        (void)mode; (void)src; (void)dst; (void)mask; (void)pcont; (void)zeroOutside;
-        return false;
-#endif
     }
 
     Csr csr() const { return Csr{N, off.p, adj.p}; }
@@ -219,15 +167,7 @@ struct Mesh {
     }
 
     // ---- class-P stages ----------------------------------------------------------------------------
-    void smooth_field(float* field, int passes) {                      // js/climate-util.js:5-25
-        if (passes <= 0) return;
-        float* src = field; float* dst = tmp.ensure(N);
-        for (int p = 0; p < passes; p++) {
-            if (!sweep_tiled(0, src, dst, nullptr, nullptr, false)) ex().for_each(N, SmoothFieldK{csr(), src, dst});
-            std::swap(src, dst);
-        }
-        if (src != field) dev_copy(field, src, sizeof(float) * (size_t)N, 2, ex().stream);
-    }
+    void smooth_field(float* field, int passes) { smooth_field_impl(*this, field, passes); }   // js/climate-util.js:5-25
 
     void warp_terrain(float* elev, double seed, double strength, const float* hotspot) {   // :233-309
         if (!(strength > 0)) return;

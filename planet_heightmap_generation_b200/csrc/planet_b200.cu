@@ -4,7 +4,7 @@
 #include "pb_engine.h"
 #include "pb_climate_engine.h"
 #include "pb_elevation_engine.h"
-#include "pb_shard.h"
+#include "pb_shardsweep.h"
 #include "pb_meshgen.h"
 #include "pb_plates.h"
 #include "pb_coarse.h"
@@ -57,11 +57,7 @@ struct pb_mesh {
 };
 
 struct pb_climate { pb::Climate c; explicit pb_climate(pb::Mesh* m) : c(m) {} };
-#if PB_CUDA
-struct pb_shard { pb::Shard s; template <class... A> explicit pb_shard(A... a) : s(a...) {} };
-#else
-struct pb_shard { int unused; };
-#endif
+struct pb_sweep_shards { pb::SweepShards s; pb_sweep_shards(pb::Mesh* m, int rank, int world) : s(m, rank, world) {} };
 
 extern "C" {
 
@@ -678,48 +674,35 @@ pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* off, int32_t* adj)
     });
 }
 
-// ---- shards ---------------------------------------------------------------------------------------------------
-pb_status pb_shard_create(pb_mesh* mesh, int32_t nOwn, int32_t myRank, int32_t world, int32_t nPeers, const int32_t* peerRanks,
-                          const int32_t* sendCounts, const int32_t* sendIdx, const int32_t* peerRecvOffset, pb_shard** out) {
+// ---- cell-range shards of the sweep loops (pb_shardsweep.h) ---------------------------------------------------------
+pb_status pb_sweep_shards_create(pb_mesh* mesh, int32_t rank, int32_t world, pb_sweep_shards** out) {
     return guard([&] {
-        need(mesh && out && nPeers >= 0 && (nPeers == 0 || (peerRanks && sendCounts && sendIdx && peerRecvOffset)), "bad argument");
-#if PB_CUDA
+        need(mesh && out, "NULL argument");
+        need(mesh->m.shards == nullptr, "the mesh already has a shard group");
         mesh->m.ctx->bind();
-        *out = new pb_shard(&mesh->m, nOwn, myRank, world, nPeers, peerRanks, sendCounts, sendIdx, peerRecvOffset);
-#else
-        (void)nOwn; (void)myRank; (void)world;
-        throw std::invalid_argument("device-side halo exchange needs the CUDA build");
-#endif
+        *out = new pb_sweep_shards(&mesh->m, rank, world);
+        mesh->m.shards = &(*out)->s;
     });
 }
-void pb_shard_destroy(pb_shard* shard) { delete shard; }
-pb_status pb_shard_export(pb_shard* shard, unsigned char* handles) {
-    return guard([&] {
-        need(shard && handles, "NULL argument");
-#if PB_CUDA
-        shard->s.m->ctx->bind(); shard->s.export_handles(handles);
-#endif
-    });
+void pb_sweep_shards_destroy(pb_sweep_shards* g) {
+    if (!g) return;
+    if (g->s.m->shards == &g->s) g->s.m->shards = nullptr;
+    delete g;
 }
-pb_status pb_shard_connect(pb_shard* shard, int32_t peerIndex, const unsigned char* handles) {
-    return guard([&] {
-        need(shard && handles, "NULL argument");
-#if PB_CUDA
-        shard->s.m->ctx->bind(); shard->s.connect(peerIndex, handles);
-#else
-        (void)peerIndex;
-#endif
-    });
+pb_status pb_sweep_shards_export(pb_sweep_shards* g, unsigned char* handles192) {
+    return guard([&] { need(g && handles192, "NULL argument"); g->s.m->ctx->bind(); g->s.export_handles(handles192); });
 }
-pb_status pb_smooth_field_sharded(pb_shard* shard, float* field, int32_t passes) {
+pb_status pb_sweep_shards_connect(pb_sweep_shards* g, int32_t peerRank, const unsigned char* handles192) {
+    return guard([&] { need(g && handles192, "NULL argument"); g->s.m->ctx->bind(); g->s.connect(peerRank, handles192); });
+}
+pb_status pb_sweep_shards_set_min_cells(pb_sweep_shards* g, int64_t minCells) {
+    return guard([&] { need(g && minCells >= 0, "bad argument"); g->s.minCells = minCells; });
+}
+pb_status pb_sweep_shards_info(pb_sweep_shards* g, int64_t* out8) {
     return guard([&] {
-        need(shard && field, "NULL argument");
-#if PB_CUDA
-        need(!shard->s.m->hostMode(), "pb_smooth_field_sharded takes device pointers (PB_POINTER_DEVICE)");
-        shard->s.m->ctx->bind(); shard->s.smooth_field(field, passes);
-#else
-        (void)passes;
-#endif
+        need(g && out8, "NULL argument");
+        out8[0] = g->s.lo; out8[1] = g->s.hi; out8[2] = (int64_t)g->s.adj.size(); out8[3] = g->s.haloBytesPerSweep;
+        out8[4] = g->s.sweepsRun; out8[5] = g->s.loopsRun; out8[6] = g->s.active() ? 1 : 0; out8[7] = g->s.minCells;
     });
 }
 

@@ -108,47 +108,52 @@ def smoothFieldSharded(dm_local, exchanger: HaloExchanger, field, passes: int):
     return field
 
 
-class PeerHaloSmoother:
-    """smoothField over the sharded mesh with the halo exchange done by the kernels themselves: every rank's buffers
-    are exported through CUDA IPC and peers store their boundary values into them over NVLink (csrc/pb_shard.h).
-    Setup exchanges the recv offsets and IPC handles once over torch.distributed; the sweeps never touch the host."""
+class SweepShardGroup:
+    """Cell-range sharding of the sweep loops of one planet across the ranks (csrc/pb_shardsweep.h).
 
-    def __init__(self, dm_local, shard: Shard):
+    Every rank builds the SAME DeviceMesh (the whole planet) and attaches a group to it; afterwards smoothField and the
+    sweep loops inside computeOceanCurrents / computePrecipitation / computeTemperature / computeWind compute only this rank's
+    cell-id range, exchange the one-cell halo by peer-memory stores inside the sweep kernels and all-gather the ranges at the
+    end of every loop.  Setup exchanges the CUDA IPC handles once (`exchange`: bytes → list of every rank's bytes; default
+    torch.distributed.all_gather_object); the sweeps never touch the host.  All ranks must issue the same calls."""
+
+    def __init__(self, dm, rank: int, world: int, exchange=None, min_cells=None):
         import ctypes as C
-
-        import torch.distributed as dist
-        self.dm, self.shard = dm_local, shard
-        lib = dm_local.lib
-        world, rank = shard.world, shard.rank
-        peers = sorted(set(shard.send) | set(shard.recv))
-        assert set(shard.send) == set(shard.recv), "the mesh graph is undirected: send and recv peers coincide"
-        # where does my block start inside each peer's local field?  (the peer's recv slice for me)
-        mine = {p: shard.recv[p][0] for p in peers}            # my recv-slice start for blocks coming from p
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine)
-        recv_offset = np.ascontiguousarray([everyone[p][rank] for p in peers], np.int32)
-        send_counts = np.ascontiguousarray([shard.send[p].size for p in peers], np.int32)
-        send_idx = np.ascontiguousarray(np.concatenate([shard.send[p] for p in peers]) if peers else np.zeros(0), np.int32)
-        peer_ranks = np.ascontiguousarray(peers, np.int32)
+        self.dm, self.rank, self.world = dm, rank, world
+        lib = dm.lib
         self._h = C.c_void_p()
-        lib.check(lib.dll.pb_shard_create(dm_local._mesh, shard.nOwn, rank, world, len(peers), peer_ranks.ctypes.data,
-                                          send_counts.ctypes.data, send_idx.ctypes.data, recv_offset.ctypes.data, C.byref(self._h)))
-        buf = (C.c_ubyte * 256)()
-        lib.check(lib.dll.pb_shard_export(self._h, buf))
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(buf))
-        for i, p in enumerate(peers):
-            hb = (C.c_ubyte * 256).from_buffer_copy(handles[p])
-            lib.check(lib.dll.pb_shard_connect(self._h, i, hb))
-        dist.barrier()
+        lib.check(lib.dll.pb_sweep_shards_create(dm._mesh, rank, world, C.byref(self._h)))
+        if min_cells is not None:
+            lib.check(lib.dll.pb_sweep_shards_set_min_cells(self._h, int(min_cells)))
+        buf = (C.c_ubyte * 192)()
+        lib.check(lib.dll.pb_sweep_shards_export(self._h, buf))
+        if exchange is None:
+            import torch.distributed as dist
 
-    def smooth(self, field, passes: int):
-        """field: torch CUDA float32 tensor with nLocal elements (owned + halo, halo current); updated in place."""
-        self.dm._begin(field)
-        self.dm.lib.check(self.dm.lib.dll.pb_smooth_field_sharded(self._h, field.data_ptr(), int(passes)))
-        return field
+            def exchange(mine):
+                everyone = [None] * world
+                dist.all_gather_object(everyone, mine)
+                return everyone
+        handles = exchange(bytes(buf))
+        for p in range(world):
+            if p == rank:
+                continue
+            hb = (C.c_ubyte * 192).from_buffer_copy(handles[p])
+            lib.check(lib.dll.pb_sweep_shards_connect(self._h, p, hb))
+        exchange(b"connected")          # nobody starts sweeping before every rank has mapped every buffer
+
+    def set_min_cells(self, n: int):
+        """planets below `n` cells keep their sweep loops unsharded (0: always shard; a huge value: never)"""
+        self.dm.lib.check(self.dm.lib.dll.pb_sweep_shards_set_min_cells(self._h, int(n)))
+
+    def info(self):
+        import ctypes as C
+        out = (C.c_int64 * 8)()
+        self.dm.lib.check(self.dm.lib.dll.pb_sweep_shards_info(self._h, out))
+        return dict(lo=int(out[0]), hi=int(out[1]), adjacent_ranks=int(out[2]), halo_bytes_per_sweep=int(out[3]),
+                    sweeps_sharded=int(out[4]), loops_sharded=int(out[5]), active=bool(out[6]), min_cells=int(out[7]))
 
     def close(self):
         if getattr(self, "_h", None):
-            self.dm.lib.dll.pb_shard_destroy(self._h)
+            self.dm.lib.dll.pb_sweep_shards_destroy(self._h)
             self._h = None

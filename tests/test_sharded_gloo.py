@@ -26,7 +26,7 @@ def _worker(rank, world, port, n_cells, passes, backend, out_dir):
     from oracle import binding as oracle
     from planet_heightmap_generation_b200._lib import Library
     from planet_heightmap_generation_b200.engine import DeviceMesh
-    from planet_heightmap_generation_b200.sharded import HaloExchanger, PeerHaloSmoother, Shard, smoothFieldSharded
+    from planet_heightmap_generation_b200.sharded import HaloExchanger, Shard, smoothFieldSharded
     from tests.conftest import make_planet
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -45,16 +45,8 @@ def _worker(rank, world, port, n_cells, passes, backend, out_dir):
     field = torch.from_numpy(sh.scatter(elev))
     if device is not None:
         field = field.to(device)
-    if backend == "peer":           # kernels store into the peers' halo slots over NVLink (csrc/pb_shard.h)
-        sm = PeerHaloSmoother(dm, sh)
-        sm.smooth(field, passes - 2)      # two calls: the epoch / "call finished" handshake is exercised too
-        sm.smooth(field, 2)
-        torch.cuda.synchronize()
-        dist.barrier()
-        sm.close()
-    else:
-        ex = HaloExchanger(sh, device)
-        smoothFieldSharded(dm, ex, field, passes)
+    ex = HaloExchanger(sh, device)
+    smoothFieldSharded(dm, ex, field, passes)
     if device is not None:
         torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"own_{rank}.npy"), sh.owned(field).cpu().numpy())
@@ -109,14 +101,3 @@ def test_sharded_smooth_field_nccl(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run(2, 20000, 6, "nccl", tmp_path)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_smooth_field_peer_memory(world, tmp_path):
-    """Device-side halo exchange (CUDA IPC peer stores + flags, no NCCL in the sweep loop), bit-exact vs the oracle.
-    world 4: the first and last shards have two peers each (the pole vertex N-1 touches the lowest ids)."""
-    import torch
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    _run(world, 20000, 7, "peer", tmp_path)
