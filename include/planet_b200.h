@@ -122,9 +122,10 @@ pb_status pb_apply_soil_creep(pb_mesh* mesh, float* r_elevation, const uint8_t* 
 
 /* runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot)
  *                                                                     js/planet-worker.js:40-102
- * Slider values as the worker receives them.  hItersOverride >= 0 replaces round(20*hydraulic)
+ * Slider values as the worker receives them.  hItersOverride > 0 replaces round(20*hydraulic)
  * while K stays 0.0006*hydraulic (BASELINE.json configs 2 and 5 ask for 50 / 200 iterations, more
- * than the UI slider can request).  Outputs: erosionDelta float32[N] (dl_erosionDelta) and, when
+ * than the UI slider can request); 0 or a negative value — so also a zero-initialised struct —
+ * means "no override" (to switch the hydraulic stage off set hydraulicErosion = 0 like the UI).  Outputs: erosionDelta float32[N] (dl_erosionDelta) and, when
  * not NULL, the r_isOcean mask the pipeline derived after the warp (uint8[N]). */
 typedef struct pb_post_params {
     double smoothing, glacialErosion, hydraulicErosion, thermalErosion, ridgeSharpening, terrainWarp;

@@ -611,7 +611,7 @@ void oracle_apply_soil_creep(const OMesh& mesh, float* r_elevation, const uint8_
     }
 }
 
-// js/planet-worker.js:40-102 — order + slider→parameter mapping.  hItersOverride >= 0 replaces
+// js/planet-worker.js:40-102 — order + slider→parameter mapping.  hItersOverride > 0 replaces
 // round(20*hydraulic) while keeping K = 0.0006*hydraulic (BASELINE configs 2 and 5).
 void oracle_run_post_processing(const OMesh& mesh, const float* r_xyz, float* r_elevation,
                                 const PostParams& p, const float* neighborDist, double seed,
@@ -628,7 +628,7 @@ void oracle_run_post_processing(const OMesh& mesh, const float* r_xyz, float* r_
     }
     if (p.glacialErosion > 0 || p.hydraulicErosion > 0 || p.thermalErosion > 0) {
         int gIters = (int)js::round(p.glacialErosion * 10);
-        int hIters = p.hItersOverride >= 0 ? p.hItersOverride : (int)js::round(p.hydraulicErosion * 20);
+        int hIters = p.hItersOverride > 0 ? p.hItersOverride : (int)js::round(p.hydraulicErosion * 20);
         double hK = p.hydraulicErosion * 0.0006;
         int tIters = (int)js::round(p.thermalErosion * 10);
         double talusSlope = 1.2 - p.thermalErosion * 0.4;

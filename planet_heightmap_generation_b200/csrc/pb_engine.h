@@ -493,7 +493,7 @@ struct Mesh {
         timer.mark(2, x.stream);
         if (p.glacialErosion > 0 || p.hydraulicErosion > 0 || p.thermalErosion > 0) {
             const int gIters = (int)js_round(p.glacialErosion * 10);
-            const int hIters = p.hItersOverride >= 0 ? p.hItersOverride : (int)js_round(p.hydraulicErosion * 20);
+            const int hIters = p.hItersOverride > 0 ? p.hItersOverride : (int)js_round(p.hydraulicErosion * 20);
             erode_composite(elev, isOcean, hIters, p.hydraulicErosion * 0.0006, 0.5, 1.0,
                             (int)js_round(p.thermalErosion * 10), 1.2 - p.thermalErosion * 0.4,
                             p.thermalErosion * 0.15, gIters, p.glacialErosion, nullptr);

@@ -43,6 +43,7 @@ class PlanetWorker:
     def __init__(self, device: int = 0, lib=None, progress=None):
         self.device, self.lib, self.progress = device, lib, progress or (lambda pct, label: None)
         self.W = None
+        self._building = None
 
     # ---- dispatch (js/planet-worker.js:944-954) ----------------------------------------------------------------------
     def onmessage(self, data: dict) -> dict:
@@ -53,15 +54,32 @@ class PlanetWorker:
             return {"type": "error", "message": f"Unknown command: {cmd}"}
         if cmd not in ("generate", "importHeightmap") and self.W is None:
             return {"type": "error", "message": f"No retained state for {cmd}"}
+        self._building = None
         try:
             return handlers[cmd](data)
         except Exception as e:      # the handlers' try/catch (:336-338)
+            # the reference assigns W only after a successful run (:277): a failed generate / import leaves the previous planet
+            # usable for reapply / editRecompute / computeClimate; the half-built mesh is released
+            if self._building is not None:
+                try:
+                    self._building.close()
+                except Exception:
+                    pass
             return {"type": "error", "message": str(e)}
+        finally:
+            self._building = None
 
     def close(self):
         if self.W is not None:
             self.W["mesh"].close()
             self.W = None
+
+    def _retain(self, new_state):
+        """W = new_state once the run has succeeded (:277-292); the planet held before is released"""
+        old, self.W = self.W, new_state
+        self._building = None
+        if old is not None and old["mesh"] is not new_state["mesh"]:
+            old["mesh"].close()
 
     # ---- shared pieces ---------------------------------------------------------------------------------------------------
     def _climate_params(self, data):          # getClimateParams (:104-110)
@@ -122,8 +140,6 @@ class PlanetWorker:
         if data.get("seed") is None:
             raise ValueError("generate needs a seed (the reference would draw Math.random())")
         seed = data["seed"]
-        self.close()
-        self.W = None
         temperatureOffset, precipitationOffset, landCoverage = self._climate_params(data)
         timing = []
 
@@ -132,7 +148,7 @@ class PlanetWorker:
 
         self.progress(0, "Shaping the world…")
         t0 = time.perf_counter()
-        mesh = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
+        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
         stage("Sphere mesh (Fibonacci + Delaunay + pole)", t0); t0 = time.perf_counter()
         neighborDist = mesh.computeNeighborDist()
         stage("Neighbor distances", t0); t0 = time.perf_counter()
@@ -187,12 +203,12 @@ class PlanetWorker:
         t0 = time.perf_counter()
         t_elevation = mesh.computeTriangleElevations(r_elevation)
         stage("Triangle elevations", t0)
-        self.W = dict(mesh=mesh, neighborDist=neighborDist, r_plate=r_plate.copy(), plateSeeds=list(plateSeeds), plateVec=plateVec,
+        self._retain(dict(mesh=mesh, neighborDist=neighborDist, r_plate=r_plate.copy(), plateSeeds=list(plateSeeds), plateVec=plateVec,
                       plateIsOcean=set(plateIsOcean), originalPlateIsOcean=set(original), plateDensity=dict(plateDensity),
                       plateDensityLand=plateDensityLand, plateDensityOcean=plateDensityOcean, prePostElev=prePostElev.copy(),
                       r_elevation_final=r_elevation.copy(), seed=seed, nMag=nMag, P=P,
                       temperatureOffset=temperatureOffset, precipitationOffset=precipitationOffset, landCoverage=landCoverage,
-                      cachedWind=wind, cachedOcean=ocean)
+                      cachedWind=wind, cachedOcean=ocean))
         reply = {"type": "done", "triangles": triangles, "halfedges": halfedges, "numRegions": mesh.numRegions,
                  "r_xyz": mesh.r_xyz, "t_xyz": t_xyz, "r_plate": r_plate, "plateSeeds": list(plateSeeds), "plateVec": plateVec,
                  "plateIsOcean": [s for s in plateSeeds if s in plateIsOcean] + [s for s in plateIsOcean if s not in plateSeeds],
@@ -221,7 +237,6 @@ class PlanetWorker:
         width, height = int(data["imageWidth"]), int(data["imageHeight"])
         if gray.size != width * height:
             raise ValueError("grayscale does not hold imageWidth * imageHeight pixels")
-        self.close()
         temperatureOffset = data.get("temperatureOffset", 0) or 0
         precipitationOffset = data.get("precipitationOffset", 0) or 0
         landCoverage = data.get("landCoverage", 0.3) if data.get("landCoverage") is not None else 0.3
@@ -231,7 +246,7 @@ class PlanetWorker:
             timing.append({"stage": name, "ms": 1e3 * (time.perf_counter() - t0)})
 
         t0 = time.perf_counter()
-        mesh = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
+        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
         stage("Sphere mesh", t0); t0 = time.perf_counter()
         neighborDist = mesh.computeNeighborDist()
         stage("Neighbor distances", t0); t0 = time.perf_counter()
@@ -265,10 +280,10 @@ class PlanetWorker:
         t_elevation = mesh.computeTriangleElevations(r_elevation)
         stage("Triangle elevations", t0)
         r_stress = np.zeros(n, np.float32)
-        self.W = dict(mesh=mesh, neighborDist=neighborDist, r_plate=r_plate.copy(), plateSeeds=list(plateSeeds), plateVec=plateVec,
+        self._retain(dict(mesh=mesh, neighborDist=neighborDist, r_plate=r_plate.copy(), plateSeeds=list(plateSeeds), plateVec=plateVec,
                       plateIsOcean=set(plateIsOcean), originalPlateIsOcean=set(plateIsOcean), plateDensity={}, plateDensityLand={},
                       plateDensityOcean={}, prePostElev=prePostElev.copy(), r_elevation_final=r_elevation.copy(), seed=seed, nMag=0,
-                      cachedWind=wind, cachedOcean=ocean)
+                      cachedWind=wind, cachedOcean=ocean))
         reply = {"type": "done", "triangles": triangles, "halfedges": halfedges, "numRegions": n, "r_xyz": mesh.r_xyz, "t_xyz": t_xyz,
                  "r_plate": r_plate, "plateSeeds": list(plateSeeds), "plateVec": plateVec,
                  "plateIsOcean": [s for s in plateSeeds if s in plateIsOcean], "originalPlateIsOcean": [s for s in plateSeeds if s in plateIsOcean],

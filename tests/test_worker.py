@@ -182,3 +182,18 @@ def test_import_heightmap_command(backend, oracle):
                                                       ridgeSharpening=0.0, terrainWarp=0.0), nd, 77, None)
     assert r2["type"] == "reapplyDone" and same(r2["r_elevation"], elev2)
     w.close()
+
+
+def test_failed_generate_keeps_previous_planet(emu_lib):
+    """js/planet-worker.js:277 assigns W only after a successful run: a failing generate must leave the retained planet usable."""
+    from planet_heightmap_generation_b200.worker import PlanetWorker
+    w = PlanetWorker(lib=emu_lib)
+    ok = w.onmessage(dict(cmd="generate", N=2000, P=8, jitter=0.75, nMag=0.4, numContinents=3, seed=7, skipClimate=True, **{k: 0.3 for k in SLIDER_KEYS}))
+    assert ok["type"] == "done"
+    bad = w.onmessage(dict(cmd="generate", N=2000, P=8, jitter=0.75, nMag=0.4, numContinents=3, seed=None, **{k: 0.3 for k in SLIDER_KEYS}))
+    assert bad["type"] == "error"
+    bad = w.onmessage(dict(cmd="generate", N=-5, P=8, jitter=0.75, nMag=0.4, numContinents=3, seed=3, **{k: 0.3 for k in SLIDER_KEYS}))
+    assert bad["type"] == "error"
+    again = w.onmessage(dict(cmd="reapply", skipClimate=True, **{k: 0.5 for k in SLIDER_KEYS}))
+    assert again["type"] == "reapplyDone", again
+    w.close()
