@@ -478,40 +478,60 @@ struct PressureDevK { const float* p; float* out; PB_DEV void operator()(int r) 
 // cells outside the mask keep their value (copyOutside) or become 0.
 struct SmoothMaskedK {
     Csr g; const uint8_t* mask; const float* src; float* dst; int zeroOutside;
-    PB_DEV void operator()(int r) const { const int b = g.off[r]; row(r, b, g.off[r + 1] - b, g.adj + b); }
+    PB_DEV void operator()(int r) const {
+        if (!mask[r]) { dst[r] = zeroOutside ? 0.0f : src[r]; return; }
+        if (g.pack) {
+            RowIds row; int deg;
+            if (row.load_packed(g.pack, r, deg)) { gathered(r, deg, row); return; }
+        }
+        const int b = g.off[r];
+        this->row(r, b, g.off[r + 1] - b, g.adj + b);
+    }
+    PB_DEV void gathered(int r, int deg, const RowIds& row) const {
+        double sum = src[r]; int count = 1;
+        float v[PB_ROW_FAST]; uint8_t mk[PB_ROW_FAST];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) { v[k] = src[row.nb[k]]; mk[k] = mask[row.nb[k]]; }
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg && mk[k]) { sum += v[k]; count++; }
+        dst[r] = (float)(sum / count);
+    }
     PB_DEV void row(int r, int b, int deg, const int* ids) const {
         (void)b;
         if (!mask[r]) { dst[r] = zeroOutside ? 0.0f : src[r]; return; }
+        if (deg <= PB_ROW_FAST) { RowIds rw; rw.load(r, deg, ids); gathered(r, deg, rw); return; }
         double sum = src[r]; int count = 1;
-        if (deg <= PB_ROW_FAST) {
-            RowIds row; row.load(r, deg, ids);
-            float v[PB_ROW_FAST]; uint8_t mk[PB_ROW_FAST];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) { v[k] = src[row.nb[k]]; mk[k] = mask[row.nb[k]]; }
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg && mk[k]) { sum += v[k]; count++; }
-        } else
-            for (int j = 0; j < deg; j++) { const int nb = ids[j]; if (mask[nb]) { sum += src[nb]; count++; } }
+        for (int j = 0; j < deg; j++) { const int nb = ids[j]; if (mask[nb]) { sum += src[nb]; count++; } }
         dst[r] = (float)(sum / count);
     }
 };
 // diffuseOceanWarmth sweep (temperature.js:33-51): cells with plate continentality >= 0.95 keep their value
 struct DiffuseWarmthK {
     Csr g; const float* pcont; const float* src; float* dst;
-    PB_DEV void operator()(int r) const { const int b = g.off[r]; row(r, b, g.off[r + 1] - b, g.adj + b); }
+    PB_DEV void operator()(int r) const {
+        if ((double)pcont[r] >= 0.95) { dst[r] = src[r]; return; }
+        if (g.pack) {
+            RowIds row; int deg;
+            if (row.load_packed(g.pack, r, deg)) { gathered(r, deg, row); return; }
+        }
+        const int b = g.off[r];
+        this->row(r, b, g.off[r + 1] - b, g.adj + b);
+    }
+    PB_DEV void gathered(int r, int deg, const RowIds& row) const {
+        double sum = src[r];
+        float v[PB_ROW_FAST];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg) sum += v[k];
+        dst[r] = (float)(sum / (deg + 1));
+    }
     PB_DEV void row(int r, int b, int deg, const int* ids) const {
         (void)b;
         if ((double)pcont[r] >= 0.95) { dst[r] = src[r]; return; }
+        if (deg <= PB_ROW_FAST) { RowIds rw; rw.load(r, deg, ids); gathered(r, deg, rw); return; }
         double sum = src[r];
-        if (deg <= PB_ROW_FAST) {
-            RowIds row; row.load(r, deg, ids);
-            float v[PB_ROW_FAST];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg) sum += v[k];
-        } else
-            for (int j = 0; j < deg; j++) sum += src[ids[j]];
+        for (int j = 0; j < deg; j++) sum += src[ids[j]];
         dst[r] = (float)(sum / (deg + 1));
     }
 };
@@ -943,34 +963,48 @@ struct EdgeWeightsK {
 // one propagation sweep (:555-571 with sign = -1, keep = min; :582-598 with sign = +1, keep = max)
 struct ShadowSweepK {
     Csr g; const uint8_t* isLand; const float* wt; const float* src; float* dst; double keepFactor; int sign;
-    PB_DEV void operator()(int r) const { const int b = g.off[r]; row(r, b, g.off[r + 1] - b, g.adj + b); }
-    PB_DEV void row(int r, int b, int deg, const int* ids) const {
+    PB_DEV void operator()(int r) const {
         const float s = src[r];
         if (!isLand[r]) { dst[r] = s; return; }
-        double val = 0, w = 0;
-        if (deg <= PB_ROW_FAST) {
-            RowIds row; row.load(r, deg, ids);
-            float wk[PB_ROW_FAST], v[PB_ROW_FAST];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) { wk[k] = k < deg ? wt[b + k] : 0.0f; v[k] = src[row.nb[k]]; }
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++)
-                if (wk[k] > 0) {
-                    const double vv = v[k];
-                    if (sign < 0 ? (vv < 0) : (vv > 0)) { val += vv * (double)wk[k]; w += (double)wk[k]; }
-                }
-        } else
-            for (int j = 0; j < deg; j++) {
-                const float wj = wt[b + j];
-                if (wj > 0) {
-                    const double v = src[ids[j]];
-                    if (sign < 0 ? (v < 0) : (v > 0)) { val += v * (double)wj; w += (double)wj; }
-                }
-            }
+        const int b = g.off[r];
+        if (g.pack) {
+            RowIds row; int deg;
+            if (row.load_packed(g.pack, r, deg)) { gathered(r, s, b, deg, row); return; }
+        }
+        this->row(r, b, g.off[r + 1] - b, g.adj + b);
+    }
+    PB_DEV void finish(int r, float s, double val, double w) const {
         if (w > 0) {
             const double carried = (val / w) * keepFactor;
             dst[r] = (float)(sign < 0 ? jmin((double)s, carried) : jmax((double)s, carried));
         } else dst[r] = s;
+    }
+    PB_DEV void gathered(int r, float s, int b, int deg, const RowIds& row) const {
+        double val = 0, w = 0;
+        float wk[PB_ROW_FAST], v[PB_ROW_FAST];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) { wk[k] = k < deg ? wt[b + k] : 0.0f; v[k] = src[row.nb[k]]; }
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++)
+            if (wk[k] > 0) {
+                const double vv = v[k];
+                if (sign < 0 ? (vv < 0) : (vv > 0)) { val += vv * (double)wk[k]; w += (double)wk[k]; }
+            }
+        finish(r, s, val, w);
+    }
+    PB_DEV void row(int r, int b, int deg, const int* ids) const {
+        const float s = src[r];
+        if (!isLand[r]) { dst[r] = s; return; }
+        if (deg <= PB_ROW_FAST) { RowIds rw; rw.load(r, deg, ids); gathered(r, s, b, deg, rw); return; }
+        double val = 0, w = 0;
+        for (int j = 0; j < deg; j++) {
+            const float wj = wt[b + j];
+            if (wj > 0) {
+                const double v = src[ids[j]];
+                if (sign < 0 ? (v < 0) : (v > 0)) { val += v * (double)wj; w += (double)wj; }
+            }
+        }
+        finish(r, s, val, w);
     }
 };
 struct KeepExtremeK {   // :572-574 / :599-601

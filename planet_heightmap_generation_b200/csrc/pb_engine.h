@@ -89,6 +89,7 @@ struct Mesh {
     int N = 0;
     long long E = 0;
     DevBuf<int> off, adj;
+    DevBuf<PackedRow> pack;            // 16-byte packed rows for the sweep family (pb_stencil.h)
     DevBuf<float> xyz, ndist;
     std::vector<int> hOffCopy, hAdjCopy;       // host CSR for the host-serial stages
     std::vector<float> hXyzCopy;
@@ -131,10 +132,15 @@ struct Mesh {
         dev_copy(xyz.ensure(3 * (size_t)n), hXyz, sizeof(float) * 3 * (size_t)n, 0, ex.stream);
         ndist.ensure(E);
         ex.for_each(N, NeighborDistK{csr(), xyz.p, ndist.p});
+        if (!getenv("PB_NO_PACKED_ROWS")) {
+            PackedRow* pk = (PackedRow*)dev_alloc(sizeof(PackedRow) * (size_t)n);      // csr() must not see it before it is filled
+            ex.for_each(N, PackRowsK{csr(), pk});
+            pack.p = pk; pack.cap = (size_t)n;
+        }
         stream_sync(ex.stream);
     }
 
-    Csr csr() const { return Csr{N, off.p, adj.p}; }
+    Csr csr() const { return Csr{N, off.p, adj.p, pack.p}; }
     const Exec& ex() const { return ctx->ex; }
     bool hostMode() const { return ctx->pointerMode == PB_POINTER_HOST; }
 

@@ -8,10 +8,38 @@
 
 namespace pb {
 
+// One 16-byte word per row next to the CSR: up to eight neighbours as signed 16-bit id deltas (nb - r), in adjacency order,
+// zero-padded (a cell is never its own neighbour).  Fibonacci ids advance in z, so every neighbour of a cell lies within
+// ±5·√N ids — 16 bits are enough up to tens of millions of cells; rows that do not fit (more than eight
+// neighbours, a larger delta: the pole vertex N-1 touches the lowest ids) carry the escape mark and are read from the CSR.
+// A sweep thread then fetches its whole row with ONE coalesced 128-bit load instead of two offsets + six to eight strided
+// 32-bit loads: 16 B per row instead of 28 B, and an order of magnitude fewer L1 wavefronts (the sweeps are LSU-bound,
+// profiles/r01_sweeps_ncu.md).
+struct alignas(16) PackedRow { uint32_t w[4]; };
+#define PB_PACK_ESCAPE 0x7fffu
+
 struct Csr {
     int N;
     const int* off;   // [N+1]
     const int* adj;   // [E]
+    const PackedRow* pack;   // [N] or nullptr
+};
+
+struct PackRowsK {
+    Csr g; PackedRow* out;
+    PB_DEV void operator()(int r) const {
+        const int b = g.off[r], deg = g.off[r + 1] - b;
+        PackedRow p; p.w[0] = PB_PACK_ESCAPE; p.w[1] = p.w[2] = p.w[3] = 0;
+        bool ok = deg <= 8;
+        uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < deg && ok; k++) {
+            const int d = g.adj[b + k] - r;
+            if (d == 0 || d > 32766 || d < -32767) ok = false;
+            else h[k] = (uint32_t)d & 0xffffu;
+        }
+        if (ok) for (int k = 0; k < 4; k++) p.w[k] = h[2 * k] | (h[2 * k + 1] << 16);
+        out[r] = p;
+    }
 };
 
 PB_DEV double or_default(double a, double b) { return (a == 0.0 || a != a) ? b : a; }  // JS `a || b`
@@ -42,24 +70,52 @@ struct RowIds {
 #pragma unroll
         for (int k = 0; k < PB_ROW_FAST; k++) nb[k] = k < deg ? ids[k] : r;
     }
+    // whole row from the packed word; false: escape row (take the CSR path)
+    PB_DEV bool load_packed(const PackedRow* pack, int r, int& deg) {
+#if PB_CUDA
+        const uint4 q = __ldg((const uint4*)(pack + r));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#else
+        const uint32_t* w = pack[r].w;
+#endif
+        if ((w[0] & 0xffffu) == PB_PACK_ESCAPE) return false;
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) {
+            const int d = (int)(int16_t)(uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+            nb[k] = r + d;
+            n += d != 0;
+        }
+        deg = n;
+        return true;
+    }
 };
 
 // js/climate-util.js:5-25 — one Laplacian sweep  dst = (src[r] + Σ src[nb]) / (deg + 1)
 struct SmoothFieldK {
     Csr g; const float* src; float* dst;
-    PB_DEV void operator()(int r) const { const int b = g.off[r]; row(r, b, g.off[r + 1] - b, g.adj + b); }
+    PB_DEV void operator()(int r) const {
+        if (g.pack) {
+            RowIds row; int deg;
+            if (row.load_packed(g.pack, r, deg)) { gathered(r, deg, row); return; }
+        }
+        const int b = g.off[r];
+        this->row(r, b, g.off[r + 1] - b, g.adj + b);
+    }
+    PB_DEV void gathered(int r, int deg, const RowIds& row) const {
+        double sum = src[r];
+        float v[PB_ROW_FAST];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg) sum += v[k];
+        dst[r] = (float)(sum / (deg + 1));
+    }
     PB_DEV void row(int r, int b, int deg, const int* ids) const {
         (void)b;
+        if (deg <= PB_ROW_FAST) { RowIds rw; rw.load(r, deg, ids); gathered(r, deg, rw); return; }
         double sum = src[r];
-        if (deg <= PB_ROW_FAST) {
-            RowIds row; row.load(r, deg, ids);
-            float v[PB_ROW_FAST];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
-#pragma unroll
-            for (int k = 0; k < PB_ROW_FAST; k++) if (k < deg) sum += v[k];
-        } else
-            for (int i = 0; i < deg; i++) sum += src[ids[i]];
+        for (int i = 0; i < deg; i++) sum += src[ids[i]];
         dst[r] = (float)(sum / (deg + 1));
     }
 };
