@@ -270,6 +270,14 @@ pb_status pb_generate_coarse_plates(pb_context* ctx, double seed, int32_t numPla
 pb_status pb_generate_fibonacci_sphere(pb_context* ctx, int32_t numPoints, double jitter, double seed, float* r_xyz);
 pb_status pb_triangulate_sphere(pb_context* ctx, int32_t numRegions, const float* r_xyz, int32_t* adjOffset, int32_t* adjList);
 pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
+/* The same mesh in the reference's OWN neighbour order: buildSphere with the published algorithm of its external
+ * dependency delaunator@5.0.1 (js/sphere-mesh.js:174-186, js/planet-worker.js:17) — stereographic projection :41-53,
+ * sweep-hull Delaunay with Delaunator's triangle numbering, addPoleToMesh :56-91, SphereMesh constructor :95-146
+ * (a row starts at the first side seen for the region, :102-106).  That numbering fixes every order-dependent stage
+ * downstream, so this is the mesh to use when the same seed must give the same planet as the web app.  Serial host
+ * algorithm (≈ 1 s per million cells); pb_mesh_create_from_points is the 4 ms device builder with a canonical row
+ * start.  r_xyz: numRegions points, the pole (0,0,1) last.  pb_mesh_get_triangles etc. return Delaunator's numbering. */
+pb_status pb_mesh_create_delaunator(pb_context* ctx, int32_t numRegions, const float* r_xyz, pb_mesh** out);
 pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* adjOffset, int32_t* adjList);
 
 /* ---- importHeightmap pieces (js/planet-worker.js:682-831) -------------------------------------------------------------

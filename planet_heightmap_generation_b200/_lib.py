@@ -82,6 +82,7 @@ SYMBOLS = {
     "pb_generate_fibonacci_sphere": (C.c_int, [_vp, _i32, C.c_double, C.c_double, _vp]),
     "pb_triangulate_sphere": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "pb_mesh_create_from_points": (C.c_int, [_vp, _i32, _vp, C.POINTER(_vp)]),
+    "pb_mesh_create_delaunator": (C.c_int, [_vp, _i32, _vp, C.POINTER(_vp)]),
     "pb_mesh_get_adjacency": (C.c_int, [_vp, _vp, _vp]),
     "pb_sweep_shards_create": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
     "pb_sweep_shards_destroy": (None, [_vp]),

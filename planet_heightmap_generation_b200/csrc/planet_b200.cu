@@ -6,6 +6,7 @@
 #include "pb_elevation_engine.h"
 #include "pb_shardsweep.h"
 #include "pb_meshgen.h"
+#include "pb_delaunator.h"
 #include "pb_plates.h"
 #include "pb_coarse.h"
 #include "pb_climate.h"
@@ -664,6 +665,36 @@ pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t n, const float* xy
         std::vector<int> hOff, hAdj;
         triangulate(ctx, n, xyz, true, &hOff, &hAdj, nullptr, nullptr);
         *out = new pb_mesh(&ctx->c, n, hOff.data(), hAdj.data(), xyz);
+    });
+}
+pb_status pb_mesh_create_delaunator(pb_context* ctx, int32_t n, const float* xyz, pb_mesh** out) {
+    return guard([&] {
+        need(ctx && xyz && out && n >= 5, "bad argument");
+        ctx->c.bind();
+        std::vector<float> hx;
+        const float* h = xyz;
+        if (ctx->c.pointerMode == PB_POINTER_DEVICE) {
+            hx.resize(3 * (size_t)n);
+            pb::dev_copy(hx.data(), xyz, sizeof(float) * hx.size(), 1, ctx->c.ex.stream);
+            pb::stream_sync(ctx->c.ex.stream);
+            h = hx.data();
+        }
+        pb::delaunator::SphereMeshHost sm;
+        try { pb::delaunator::build_sphere(h, n, sm); }
+        catch (const std::invalid_argument&) { throw; }
+        catch (const std::exception& e) { throw pb::Error(e.what()); }
+        std::unique_ptr<pb_mesh> mesh(new pb_mesh(&ctx->c, n, sm.adjOffset.data(), sm.adjList.data(), h));
+        // the triangle arrays keep Delaunator's numbering too (worker replies: triangles, halfedges, t_xyz, t_elevation)
+        pb::MeshTriangles& t = mesh->triangles;
+        const size_t S = sm.triangles.size();
+        if ((long long)S != 3ll * (2ll * n - 4)) throw pb::Error("Delaunator mesh is not a closed triangulated sphere");
+        const cudaStream_t st = ctx->c.ex.stream;
+        pb::dev_copy(t.tri.ensure(S), sm.triangles.data(), sizeof(int) * S, 0, st);
+        pb::dev_copy(t.half.ensure(S), sm.halfedges.data(), sizeof(int) * S, 0, st);
+        pb::dev_copy(t.adjTri.ensure(sm.adjTri.size()), sm.adjTri.data(), sizeof(int) * sm.adjTri.size(), 0, st);
+        pb::stream_sync(st);
+        t.T = (int)(S / 3);
+        *out = mesh.release();
     });
 }
 pb_status pb_mesh_get_adjacency(const pb_mesh* mesh, int32_t* off, int32_t* adj) {

@@ -45,21 +45,26 @@ class DeviceMesh:
         self._mode = _lib.POINTER_HOST
 
     @classmethod
-    def from_points(cls, r_xyz, device: int = 0, lib: Library | None = None) -> "DeviceMesh":
+    def from_points(cls, r_xyz, device: int = 0, lib: Library | None = None, order: str = "canonical") -> "DeviceMesh":
         """buildSphere's triangulation on the device (js/sphere-mesh.js:174-186 → csrc/pb_meshgen.h): r_xyz holds the
-        unit vectors of all regions, pole vertex included; adjOffset / adjList come back from the GPU."""
+        unit vectors of all regions, pole vertex included; adjOffset / adjList come back from the GPU.
+        order="delaunator": the reference's own neighbour order (Delaunator 5.0.1's triangle numbering, host algorithm)."""
         self = cls.__new__(cls)
         self.lib = lib or default_library()
         self.device = device
         self._ctx = C.c_void_p()
         self._mesh = None
         self.lib.check(self.lib.dll.pb_context_create(device, C.byref(self._ctx)))
-        return self._finish_from_points(r_xyz)
+        return self._finish_from_points(r_xyz, order)
 
     @classmethod
-    def build_sphere(cls, N: int, jitter: float, seed: float, device: int = 0, lib: Library | None = None) -> "DeviceMesh":
+    def build_sphere(cls, N: int, jitter: float, seed: float, device: int = 0, lib: Library | None = None,
+                     order: str = "canonical") -> "DeviceMesh":
         """buildSphere(N, jitter, rng) (js/sphere-mesh.js:174-186) entirely on the device: Fibonacci points with
-        makeRng(seed) jitter + the pole vertex, then the triangulation.  The result carries r_xyz, adjOffset, adjList."""
+        makeRng(seed) jitter + the pole vertex, then the triangulation.  The result carries r_xyz, adjOffset, adjList.
+        order="canonical" (default): device builder, every neighbour row starts at a canonical triangle;
+        order="delaunator": rows start where the reference's SphereMesh constructor starts them (Delaunator 5.0.1's triangle
+        numbering, a serial host algorithm) — same seed, same planet as the web app."""
         self = cls.__new__(cls)
         self.lib = lib or default_library()
         self.device = device
@@ -68,7 +73,7 @@ class DeviceMesh:
         self.lib.check(self.lib.dll.pb_context_create(device, C.byref(self._ctx)))
         xyz = np.empty(3 * (int(N) + 1), np.float32)
         self.lib.check(self.lib.dll.pb_generate_fibonacci_sphere(self._ctx, int(N), float(jitter), float(seed), xyz.ctypes.data))
-        return self._finish_from_points(xyz)
+        return self._finish_from_points(xyz, order)
 
     @classmethod
     def _adopt(cls, parent: "DeviceMesh", mesh_handle, r_xyz) -> "DeviceMesh":
@@ -87,12 +92,15 @@ class DeviceMesh:
         self._mode = parent._mode
         return self
 
-    def _finish_from_points(self, r_xyz):
+    def _finish_from_points(self, r_xyz, order="canonical"):
+        if order not in ("canonical", "delaunator"):
+            raise ValueError("order must be 'canonical' or 'delaunator'")
         self.r_xyz = np.ascontiguousarray(r_xyz, np.float32).reshape(-1)
         self.numRegions = self.r_xyz.shape[0] // 3
         self._mesh = C.c_void_p()
         d = self.lib.dll
-        self.lib.check(d.pb_mesh_create_from_points(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
+        create = d.pb_mesh_create_delaunator if order == "delaunator" else d.pb_mesh_create_from_points
+        self.lib.check(create(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
         self.numEdges = int(d.pb_mesh_num_edges(self._mesh))
         self.adjOffset = np.empty(self.numRegions + 1, np.int32)
         self.adjList = np.empty(self.numEdges, np.int32)
