@@ -59,7 +59,11 @@ pb_status pb_synchronize(pb_context* ctx);
  * one serial chain of heap pops whose tie order depends on the heap layout.  "host" (default): on a host core, like
  * the other host-serial stages (assignDistanceField); "device": the one-CTA CUDA kernel k_flood_heap (≈ 8x slower:
  * a single warp retires the dependent chain at ~0.1 instructions per cycle).  Everything else of the function stays
- * on the GPU either way and the results are identical. */
+ * on the GPU either way and the results are identical.
+ * "mesh_order": "canonical" (default) — pb_triangulate_sphere / pb_mesh_create_from_points / the coarse mesh of
+ * pb_generate_coarse_plates use the device mesh builder, whose neighbour rows start at a canonical triangle; "delaunator" —
+ * they use the reference's own row starts (delaunator@5.0.1's triangle numbering, serial host algorithm, see
+ * pb_mesh_create_delaunator): same seed, same planet as the web app. */
 pb_status pb_set_option(pb_context* ctx, const char* name, const char* value);
 /* kernels launched by this library on any context since process start (bench: gpu_launches) */
 int64_t pb_launch_count(void);

@@ -19,6 +19,7 @@ inline double js_round(double x) { return floor(x + 0.5); }   // Math.round
 struct Context {
     int device = 0;
     int pointerMode = PB_POINTER_HOST;
+    bool meshOrderDelaunator = false;   // option "mesh_order": "canonical" (device builder) | "delaunator" (reference's own row starts, host)
     bool floodOnHost = true;       // option "flood": "host" (default) = the serial heap pass of priorityFloodCarve on a host core, "device" = k_flood_heap
     Exec ex;
     DevBuf<int> ticket;

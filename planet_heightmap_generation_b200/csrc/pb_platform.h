@@ -82,9 +82,10 @@ inline void dev_memset(void* p, int v, size_t bytes, cudaStream_t s) {
     memset(p, v, bytes);
 #endif
 }
-// kind: 0 h2d, 1 d2h, 2 d2d
+// kind: 0 h2d, 1 d2h, 2 d2d, 3 h2h
 inline void dev_copy(void* dst, const void* src, size_t bytes, int kind, cudaStream_t s) {
     if (bytes == 0) return;
+    if (kind == 3) { memmove(dst, src, bytes); return; }
 #if PB_CUDA
     cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     PB_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, k, s));
@@ -287,7 +288,10 @@ struct ProfScope {
     cudaStream_t s;
     cudaEvent_t a, b;
     const char* name;
+    bool trace = false;
+    static bool tracing() { static const bool t = getenv("PB_TRACE") != nullptr; return t; }   // diagnostic: name + sync per launch
     ProfScope(Profiler* prof, const char* nm, cudaStream_t st) : s(st), name(nm) {
+        if (tracing()) { trace = true; fprintf(stderr, "[pb trace] %s ...", nm); fflush(stderr); }
         if (prof && prof->wants(nm)) {
             p = prof;
             a = p->get(); b = p->get();
@@ -296,6 +300,7 @@ struct ProfScope {
     }
     ~ProfScope() {
         if (p) { cudaEventRecord(b, s); p->recs.push_back({name, a, b}); }
+        if (trace) { const cudaError_t e = cudaStreamSynchronize(s); fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e)); fflush(stderr); }
     }
 #else
     ProfScope(Profiler*, const char*, cudaStream_t) {}

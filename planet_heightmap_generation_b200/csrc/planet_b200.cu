@@ -106,6 +106,9 @@ pb_status pb_set_option(pb_context* ctx, const char* name, const char* value) {
         if (n == "flood") {
             need(v == "device" || v == "host", "flood must be 'device' or 'host'");
             ctx->c.floodOnHost = v == "host";
+        } else if (n == "mesh_order") {
+            need(v == "canonical" || v == "delaunator", "mesh_order must be 'canonical' or 'delaunator'");
+            ctx->c.meshOrderDelaunator = v == "delaunator";
         } else throw std::invalid_argument("unknown option: " + n);
     });
 }
@@ -622,6 +625,21 @@ static void triangulate(pb_context* ctx, int n, const float* xyz, bool hostPtrs,
     if (n < 4) throw std::invalid_argument("a sphere mesh needs at least 4 points");
     const pb::Exec& ex = ctx->c.ex;
     const size_t E = 6 * (size_t)n - 12;
+    if (ctx->c.meshOrderDelaunator) {
+        // option mesh_order = delaunator: the reference's own neighbour order (host algorithm, pb_delaunator.h)
+        std::vector<float> hx;
+        const float* h = xyz;
+        if (!hostPtrs) { hx.resize(3 * (size_t)n); pb::dev_copy(hx.data(), xyz, sizeof(float) * hx.size(), 1, ex.stream); pb::stream_sync(ex.stream); h = hx.data(); }
+        pb::delaunator::SphereMeshHost sm;
+        try { pb::delaunator::build_sphere(h, n, sm); }
+        catch (const std::invalid_argument&) { throw; }
+        catch (const std::exception& e) { throw pb::Error(e.what()); }
+        if (sm.adjList.size() != E) throw pb::Error("Delaunator mesh is not a closed triangulated sphere");
+        if (outOff) { pb::dev_copy(outOff, sm.adjOffset.data(), sizeof(int) * ((size_t)n + 1), hostPtrs ? 3 : 0, ex.stream);
+                      pb::dev_copy(outAdj, sm.adjList.data(), sizeof(int) * E, hostPtrs ? 3 : 0, ex.stream); pb::stream_sync(ex.stream); }
+        if (hOff) { *hOff = sm.adjOffset; *hAdj = sm.adjList; }
+        return;
+    }
     pb::DevBuf<float>& dXyz = ctx->triXyz; pb::DevBuf<int>& dOff = ctx->triOff; pb::DevBuf<int>& dAdj = ctx->triAdj;
     const float* px = xyz;
     if (hostPtrs) { pb::dev_copy(dXyz.ensure(3 * (size_t)n), xyz, sizeof(float) * 3 * (size_t)n, 0, ex.stream); px = dXyz.p; }
@@ -658,7 +676,9 @@ pb_status pb_triangulate_sphere(pb_context* ctx, int32_t n, const float* xyz, in
         triangulate(ctx, n, xyz, ctx->c.pointerMode == PB_POINTER_HOST, nullptr, nullptr, off, adj);
     });
 }
+pb_status pb_mesh_create_delaunator(pb_context* ctx, int32_t n, const float* xyz, pb_mesh** out);
 pb_status pb_mesh_create_from_points(pb_context* ctx, int32_t n, const float* xyz, pb_mesh** out) {
+    if (ctx && ctx->c.meshOrderDelaunator) return pb_mesh_create_delaunator(ctx, n, xyz, out);
     return guard([&] {
         need(ctx && xyz && out, "NULL argument");
         ctx->c.bind();

@@ -99,8 +99,9 @@ class DeviceMesh:
         self.numRegions = self.r_xyz.shape[0] // 3
         self._mesh = C.c_void_p()
         d = self.lib.dll
-        create = d.pb_mesh_create_delaunator if order == "delaunator" else d.pb_mesh_create_from_points
-        self.lib.check(create(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
+        # the option stays on the context: the coarse mesh of generateCoarsePlates follows the same order
+        self.lib.check(d.pb_set_option(self._ctx, b"mesh_order", order.encode()))
+        self.lib.check(d.pb_mesh_create_from_points(self._ctx, self.numRegions, self.r_xyz.ctypes.data, C.byref(self._mesh)))
         self.numEdges = int(d.pb_mesh_num_edges(self._mesh))
         self.adjOffset = np.empty(self.numRegions + 1, np.int32)
         self.adjList = np.empty(self.numEdges, np.int32)
