@@ -63,36 +63,8 @@ struct AccumulateK {
         const int r = order[i];
         const int b = g.off[r], e = g.off[r + 1];
         float acc = initv ? initv[r] : 1.0f;
-        // donors that ran before this item, sorted by position — found BEFORE any polling (nothing here depends on other
-        // items), so that once the last donor's word arrives only the additions are left on the dependency chain
-        const int CAP = 12;
-        int dp[CAP], dd[CAP];
-        int n = 0;
-        bool fits = true;
-        for (int j = b; j < e; j++) {
-            const int d = g.adj[j];
-            const int p = pos[d];
-            if (target[d] != r || p < 0 || p >= i) continue;
-            if (n == CAP) { fits = false; break; }
-            int k = n++;
-            while (k > 0 && dp[k - 1] > p) { dp[k] = dp[k - 1]; dd[k] = dd[k - 1]; k--; }
-            dp[k] = p; dd[k] = d;
-        }
-        if (fits) {
-            unsigned long long w[CAP];
-            bool ok = false;
-            for (int s = 0; s < PB_SPIN && !ok; s++) {
-                ok = true;
-                for (int k = 0; k < n; k++) { w[k] = ld_word(contrib + dd[k]); }     // independent loads: one L2 round trip for all donors
-                for (int k = 0; k < n; k++) if (!word_seq(w[k])) ok = false;
-            }
-            if (!ok) return false;
-            for (int k = 0; k < n; k++) acc = (float)((double)acc + (double)word_value(w[k]));
-            st_word(contrib + r, make_word(acc, 1));
-            return true;
-        }
         int last = -1;
-        for (;;) {     // more donors than the local list holds: repeated-min over the row, each donor's word polled directly
+        for (;;) {     // donors in position order (repeated-min: degree is tiny); each donor's word is polled directly
             int bp = 0x7fffffff, bd = -1;
             for (int j = b; j < e; j++) {
                 const int d = g.adj[j];
