@@ -313,7 +313,7 @@ struct Mesh {
                         liftUp.p, levels, N, dIn, carveStrength};
         launch_stats().launches++;
         ProfScope ps(x.prof, "pb::k_carve_lift", x.stream);
-        k_carve_lift<<<(nSeg + PB_CARVE_WARPS - 1) / PB_CARVE_WARPS, PB_CARVE_THREADS, 0, x.stream>>>(a);
+        k_carve_lift<<<nSeg, PB_CARVE_THREADS, 0, x.stream>>>(a);
         PB_CUDA_CHECK(cudaGetLastError());
     }
 #endif

@@ -656,96 +656,117 @@ struct CarveLiftArgs {
     const uint8_t* isOcean; const float* surface; float* elev;
     const int* up; int levels; int N; const int* depth; double carveStrength;
 };
-#define PB_CARVE_WARPS 4            // flood trees per CTA: one warp each
-#define PB_CARVE_THREADS (32 * PB_CARVE_WARPS)
-#define PB_CARVE_PATH_CAP 1024
+#define PB_CARVE_THREADS 256
+#define PB_CARVE_PATH_CAP 2048
 
 __device__ __forceinline__ int lift_ancestor(const int* up, int N, int c, int j) {
     for (int k = 0; j; k++, j >>= 1) if (j & 1) c = __ldg(up + (size_t)k * N + c);
     return c;
 }
 
-// One WARP per flood tree (the cells of a tree are processed in ascending id, one after the other, so the pass is a
-// chain of |filled cells of the largest tree| steps: what counts is the latency of one step).  Per step: the 32 lanes
-// look at the next 32 cells of the tree for a deficit (ballot), fetch the path of the first one by binary lifting
-// (L1-resident table), reduce the peak with shuffles, form the kernel terms in parallel and add them in the reference's
-// order, then apply the window.  No block-wide barrier, ≈ 1 µs per filled cell instead of ≈ 6 µs for the CTA-per-tree form.
+// One CTA per flood tree: the cells of a tree are processed in ascending id, one after the other, and at a million cells a
+// drainTo path to the coast is hundreds of cells long, so each step spreads its path over 256 lanes.  (A warp-per-tree form
+// without block barriers was measured 2x SLOWER at 1M cells — 53 ms instead of 26 ms per launch: its 32 lanes need 8x more
+// dependent binary-lifting rounds per path, which costs more than the barriers it saves.)
 __global__ void __launch_bounds__(PB_CARVE_THREADS) k_carve_lift(CarveLiftArgs a) {
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int s = blockIdx.x * PB_CARVE_WARPS + wib;
+    const int s = blockIdx.x;
     if (s >= *a.nSeg) return;
     const int segB = a.segStart[s];
     const int segE = (s + 1 < *a.nSeg) ? a.segStart[s + 1] : *a.nCells;
-    __shared__ int sPathAll[PB_CARVE_WARPS][PB_CARVE_PATH_CAP];      // ancestors of the current cell (the window pass reuses them)
-    __shared__ double sTermAll[PB_CARVE_WARPS][32];
-    int* sPath = sPathAll[wib];
-    double* sTerm = sTermAll[wib];
-    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int sFirst;
+    __shared__ double sRedH[PB_CARVE_THREADS / 32];
+    __shared__ int sRedJ[PB_CARVE_THREADS / 32];
+    __shared__ double sTerm[PB_CARVE_THREADS];
+    __shared__ double sKernelSum;
+    __shared__ int sPath[PB_CARVE_PATH_CAP];      // ancestors of the current cell (the window pass reuses them)
     int q0 = segB;
     while (q0 < segE) {
-        // next cell (ascending id) whose CURRENT deficit exceeds EPS
-        const int q = q0 + lane;
-        int rl = -1; double dl = 0;
-        if (q < segE) { rl = __ldg(a.cells + q); dl = (double)__ldg(a.surface + rl) - (double)__ldcg(a.elev + rl); }
-        const unsigned hit = __ballot_sync(FULL, dl > PB_FLOOD_EPS);
-        if (!hit) { q0 += 32; continue; }
-        const int first = __ffs(hit) - 1;
-        const int r = __shfl_sync(FULL, rl, first);
-        const double deficit = __shfl_sync(FULL, dl, first);
-        const int qf = q0 + first;
-        const int len = __ldg(a.depth + r) + 1;
+        // find the next cell (ascending id) whose current deficit exceeds EPS
+        if (tid == 0) sFirst = 0x7fffffff;
+        __syncthreads();
+        {
+            const int q = q0 + tid;
+            if (q < segE) {
+                const int r = a.cells[q];
+                const double deficit = (double)__ldg(a.surface + r) - (double)__ldcg(a.elev + r);
+                if (deficit > PB_FLOOD_EPS) atomicMin(&sFirst, q);
+            }
+        }
+        __syncthreads();
+        const int qf = sFirst;
+        if (qf == 0x7fffffff) { q0 += PB_CARVE_THREADS; __syncthreads(); continue; }
+        const int r = a.cells[qf];
+        const double deficit = (double)__ldg(a.surface + r) - (double)__ldcg(a.elev + r);
+        const int len = a.depth[r] + 1;
         // peak = first maximum along the path (strict >)
         double bh = -INFINITY; int bj = 0x7fffffff;
-        for (int j = lane; j < len; j += 32) {
+        for (int j = tid; j < len; j += PB_CARVE_THREADS) {
             const int c = lift_ancestor(a.up, a.N, r, j);
             if (j < PB_CARVE_PATH_CAP) sPath[j] = c;
             const double h = (double)__ldcg(a.elev + c);
             if (h > bh) { bh = h; bj = j; }
         }
         for (int o = 16; o; o >>= 1) {
-            const double oh = __shfl_xor_sync(FULL, bh, o);
-            const int oj = __shfl_xor_sync(FULL, bj, o);
+            const double oh = __shfl_down_sync(0xffffffffu, bh, o);
+            const int oj = __shfl_down_sync(0xffffffffu, bj, o);
             if (oh > bh || (oh == bh && oj < bj)) { bh = oh; bj = oj; }
         }
-        const int peakIdx = bj;
-        __syncwarp();
-        if (peakIdx == 0x7fffffff) { q0 = qf + 1; continue; }   // all-NaN path: the reference skips the cell
+        if (lane == 0) { sRedH[warp] = bh; sRedJ[warp] = bj; }
+        __syncthreads();
+        int peakIdx;
+        {
+            double h = sRedH[0]; int j = sRedJ[0];
+            for (int w = 1; w < PB_CARVE_THREADS / 32; w++)
+                if (sRedH[w] > h || (sRedH[w] == h && sRedJ[w] < j)) { h = sRedH[w]; j = sRedJ[w]; }
+            peakIdx = j;
+        }
+        if (peakIdx == 0x7fffffff) { q0 = qf + 1; __syncthreads(); continue; }   // all-NaN path: reference skips the cell
         const double carveAmount = deficit * a.carveStrength;
         double rad = ceil(len * 0.3);
         if (rad < 3) rad = 3;
         const int radius = (int)rad;
         const int startIdx = peakIdx - radius > 0 ? peakIdx - radius : 0;
         const int endIdx = peakIdx + radius < len - 1 ? peakIdx + radius : len - 1;
-        // kernelSum is a sequential double sum in the reference: terms in parallel, the additions in order (every lane
-        // adds the same values in the same order, so all lanes hold the same sum)
+        // kernelSum is a sequential double sum in the reference: terms in parallel, sum by one thread
         double ksum = 0;
-        for (int base = startIdx; base <= endIdx; base += 32) {
-            const int k = base + lane;
+        for (int base = startIdx; base <= endIdx; base += PB_CARVE_THREADS) {
+            const int k = base + tid;
             if (k <= endIdx) {
                 const double dist = k > peakIdx ? k - peakIdx : peakIdx - k;
-                sTerm[lane] = 1 - dist / (radius + 1);
+                sTerm[tid] = 1 - dist / (radius + 1);
             }
-            __syncwarp();
-            const int cnt = endIdx - base + 1 < 32 ? endIdx - base + 1 : 32;
-            for (int t = 0; t < cnt; t++) ksum += sTerm[t];
-            __syncwarp();
+            __syncthreads();
+            if (tid == 0) {
+                const int cnt = endIdx - base + 1 < PB_CARVE_THREADS ? endIdx - base + 1 : PB_CARVE_THREADS;
+                int t = 0;
+                for (; t + 8 <= cnt; t += 8) {       // loads issued together; the additions stay in sequence
+                    const double v0 = sTerm[t], v1 = sTerm[t + 1], v2 = sTerm[t + 2], v3 = sTerm[t + 3];
+                    const double v4 = sTerm[t + 4], v5 = sTerm[t + 5], v6 = sTerm[t + 6], v7 = sTerm[t + 7];
+                    ksum += v0; ksum += v1; ksum += v2; ksum += v3; ksum += v4; ksum += v5; ksum += v6; ksum += v7;
+                }
+                for (; t < cnt; t++) ksum += sTerm[t];
+                sKernelSum = ksum;
+            }
+            __syncthreads();
         }
-        if (ksum > 0) {
-            for (int k = startIdx + lane; k <= endIdx; k += 32) {
+        const double kernelSum = sKernelSum;
+        if (kernelSum > 0) {
+            for (int k = startIdx + tid; k <= endIdx; k += PB_CARVE_THREADS) {
                 const int c = k < PB_CARVE_PATH_CAP ? sPath[k] : lift_ancestor(a.up, a.N, r, k);
                 const double dist = k > peakIdx ? k - peakIdx : peakIdx - k;
-                const double weight = (1 - dist / (radius + 1)) / ksum;
+                const double weight = (1 - dist / (radius + 1)) / kernelSum;
                 float v = (float)((double)__ldcg(a.elev + c) - carveAmount * weight);
                 if (v < 0) v = 0;
                 __stcg(a.elev + c, v);
             }
         }
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (tid == 0) {
             const double fillAmount = deficit * (1 - a.carveStrength);
             __stcg(a.elev + r, (float)((double)__ldcg(a.elev + r) + fillAmount));
         }
-        __syncwarp();
+        __syncthreads();
         q0 = qf + 1;
     }
 }
