@@ -533,14 +533,18 @@ def sharded_climate_probe(args, rank, world, local, cells, steps=2):
     ms_one, out = run(steps)
     st = cl._state(dm)
     keys = ("r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter", "r_ocean_warmth_summer")
-    ref = {k: torch.from_numpy(st.field(k)) for k in keys}
+    def field(k):
+        v = st.field(k)
+        return v.clone() if isinstance(v, torch.Tensor) else torch.from_numpy(np.array(v, copy=True))
+
+    ref = {k: field(k) for k in keys}
     ref_koppen = koppen.clone()
     group.set_min_cells(0)
     before = group.info()
     run(1)
     ms_sh, out = run(steps)
     info = group.info()
-    same = bool((koppen == ref_koppen).all().item()) and all(bool((torch.from_numpy(st.field(k)) == ref[k]).all().item()) for k in keys)
+    same = bool((koppen == ref_koppen).all().item()) and all(bool((field(k) == ref[k]).all().item()) for k in keys)
     flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

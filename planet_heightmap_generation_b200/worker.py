@@ -40,8 +40,11 @@ def _mask_to_list(mask) -> list:
 
 
 class PlanetWorker:
-    def __init__(self, device: int = 0, lib=None, progress=None):
+    def __init__(self, device: int = 0, lib=None, progress=None, mesh_order: str = "canonical"):
+        """mesh_order: "canonical" (device mesh builder) or "delaunator" (the reference's own neighbour order — same seed,
+        same planet as the web app; host algorithm, see DeviceMesh.build_sphere)."""
         self.device, self.lib, self.progress = device, lib, progress or (lambda pct, label: None)
+        self.mesh_order = mesh_order
         self.W = None
         self._building = None
 
@@ -148,7 +151,7 @@ class PlanetWorker:
 
         self.progress(0, "Shaping the world…")
         t0 = time.perf_counter()
-        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
+        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib, order=self.mesh_order)
         stage("Sphere mesh (Fibonacci + Delaunay + pole)", t0); t0 = time.perf_counter()
         neighborDist = mesh.computeNeighborDist()
         stage("Neighbor distances", t0); t0 = time.perf_counter()
@@ -246,7 +249,7 @@ class PlanetWorker:
             timing.append({"stage": name, "ms": 1e3 * (time.perf_counter() - t0)})
 
         t0 = time.perf_counter()
-        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib)
+        mesh = self._building = DeviceMesh.build_sphere(N, jitter, seed, device=self.device, lib=self.lib, order=self.mesh_order)
         stage("Sphere mesh", t0); t0 = time.perf_counter()
         neighborDist = mesh.computeNeighborDist()
         stage("Neighbor distances", t0); t0 = time.perf_counter()

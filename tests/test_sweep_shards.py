@@ -39,6 +39,13 @@ def _rank_body(lib, rank, world, exchange, mesh, xyz, elev, r_plate, pio, passes
     from planet_heightmap_generation_b200.climate_util import smoothField
     from planet_heightmap_generation_b200.engine import DeviceMesh
     from planet_heightmap_generation_b200.sharded import SweepShardGroup
+    if exchange is None:             # one process per rank: torch.distributed carries the handles
+        import torch.distributed as dist
+
+        def exchange(mine):
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            return everyone
     dm = DeviceMesh(mesh, xyz, device=device, lib=lib)
     grp = SweepShardGroup(dm, rank, world, exchange=exchange, min_cells=0)
     f = elev.copy()

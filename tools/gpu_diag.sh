@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T="tests/test_delaunator.py::test_pipeline_parity_on_delaunator_mesh"
-timeout 40 python -m pytest "$T" -m gpu -x -q > gpurun_out/diag_plain.log 2>&1; echo "rc=$?" >> gpurun_out/diag_plain.log
-tail -c 400 gpurun_out/diag_plain.log
+timeout 150 python bench.py --workload climate --cells 10000000 --steps 2 --warmup 1 --no-cpu > gpurun_out/ab_packed.json 2> gpurun_out/ab_packed.log; echo "rc=$?" >> gpurun_out/ab_packed.log
+PB_NO_PACKED_ROWS=1 timeout 150 python bench.py --workload climate --cells 10000000 --steps 2 --warmup 1 --no-cpu > gpurun_out/ab_csr.json 2> gpurun_out/ab_csr.log; echo "rc=$?" >> gpurun_out/ab_csr.log
+grep -A12 "per-kernel device time" gpurun_out/ab_packed.log | head -14; grep -A12 "per-kernel device time" gpurun_out/ab_csr.log | head -14
