@@ -454,8 +454,21 @@ struct Mesh {
             if (hydraulicThisIter) {
                 if (glacialThisIter) sort_land_desc(elev, landCount);
                 x.for_each(N, ReceiversK{g, elev, isOcean, ndist.p, drainTarget.p, cellDist.p});
-                dev_memset(words.p, 0, sizeof(unsigned long long) * (size_t)N, x.stream);
-                x.ordered(landCount, AccumulateK{g, order.p, pos.p, drainTarget.p, isOcean, nullptr, words.p});
+                if (landCount < (1 << 24) && !getenv("PB_ORDERED_FLOW")) {
+                    // integer-valued, exact in f32: subtree sizes by pointer doubling (pb_erode.h)
+                    int* jA = k0.p; int* jB = k1.p; int* cA = k2.p; int* cB = cnt.p;       // free until SolvePrepK
+                    x.for_each(landCount, SubtreeInitK{order.p, pos.p, drainTarget.p, isOcean, jA, cA});
+                    int rounds = 1; while ((1ll << rounds) < (long long)landCount + 1) rounds++;
+                    for (int k = 0; k < rounds; k++) {
+                        x.for_each(landCount, SubtreeCopyK{order.p, cA, cB});
+                        x.for_each(landCount, SubtreeRoundK{order.p, jA, jB, cA, cB});
+                        std::swap(jA, jB); std::swap(cA, cB);
+                    }
+                    x.for_each(landCount, SubtreeWordsK{order.p, cA, words.p});
+                } else {
+                    dev_memset(words.p, 0, sizeof(unsigned long long) * (size_t)N, x.stream);
+                    x.ordered(landCount, AccumulateK{g, order.p, pos.p, drainTarget.p, isOcean, nullptr, words.p});
+                }
                 x.for_each(N, AccumulateFinalK{g, pos.p, drainTarget.p, isOcean, nullptr, words.p, flow.p, nullptr});
                 if (taps && iter == taps->captureIter) {
                     if (taps->drainTarget) dev_copy(taps->drainTarget, drainTarget.p, sizeof(int) * (size_t)N, 2, x.stream);

@@ -83,6 +83,43 @@ struct AccumulateK {
         return true;
     }
 };
+// Hydraulic flow accumulation without the dependency chain.  With init = 1 every contribution is an integer below 2^24
+// (as long as there are fewer than 16.7M land cells), so the reference's f32 additions (:604-611) are exact and the order of
+// the additions cannot matter: contrib[v] — the value v hands to its receiver when the descending sweep reaches it — is the
+// number of cells in v's subtree of the forest of EARLY edges (d → target[d] with pos[d] < pos[target[d]]: a donor that sits
+// later in the order adds to its receiver only after the receiver has already passed its own value on; AccumulateFinalK adds
+// those late donors to the final flow).  Subtree sizes by pointer doubling: after round k, cnt[v] = descendants within
+// distance < 2^k, jump[u] = 2^k-th ancestor; ⌈log2(land)⌉ rounds of one integer atomicAdd per cell instead of a chain of
+// |longest river| dependent polls (0.58 ms → ≈ 0.1 ms per iteration at 1M cells).
+struct SubtreeInitK {
+    const int* order; const int* pos; const int* target; const uint8_t* isOcean; int* jump; int* cnt;
+    PB_DEV void operator()(int i) const {
+        const int r = order[i];
+        const int t = target[r];
+        int j = -1;
+        if (t >= 0 && !isOcean[t] && pos[t] > i) j = t;
+        jump[r] = j; cnt[r] = 1;
+    }
+};
+struct SubtreeCopyK {   // next = cur for the land cells (the round then adds the far descendants)
+    const int* order; const int* cur; int* next;
+    PB_DEV void operator()(int i) const { const int r = order[i]; next[r] = cur[r]; }
+};
+struct SubtreeRoundK {
+    const int* order; const int* jumpIn; int* jumpOut; const int* cntIn; int* cntOut;
+    PB_DEV void operator()(int i) const {
+        const int r = order[i];
+        const int j = jumpIn[r];
+        int jj = -1;
+        if (j >= 0) { atomic_add(cntOut + j, cntIn[r]); jj = jumpIn[j]; }
+        jumpOut[r] = jj;
+    }
+};
+struct SubtreeWordsK {
+    const int* order; const int* cnt; unsigned long long* contrib;
+    PB_DEV void operator()(int i) const { const int r = order[i]; contrib[r] = make_word((float)cnt[r], 1); }
+};
+
 // final value: init + every donor's contribution in position order; also the donor count (mod 256)
 struct AccumulateFinalK {
     Csr g; const int* pos; const int* target; const uint8_t* isOcean; const float* initv;
