@@ -268,6 +268,7 @@ struct Mesh {
     DevBuf<HeapEntry> heapSpill;
     DevBuf<int> liftUp, liftDepthA, liftDepthB;
     int floodSmemMax = -1;
+    int subtreeGrid = -1;
     int lastMaxHeap = 0;
     void flood_heap_cuda(const float* elev) {
         const Exec& x = ex();
@@ -457,14 +458,33 @@ struct Mesh {
                 if (landCount < (1 << 24) && !getenv("PB_ORDERED_FLOW")) {
                     // integer-valued, exact in f32: subtree sizes by pointer doubling (pb_erode.h)
                     int* jA = k0.p; int* jB = k1.p; int* cA = k2.p; int* cB = cnt.p;       // free until SolvePrepK
-                    x.for_each(landCount, SubtreeInitK{order.p, pos.p, drainTarget.p, isOcean, jA, cA});
-                    int rounds = 1; while ((1ll << rounds) < (long long)landCount + 1) rounds++;
-                    for (int k = 0; k < rounds; k++) {
-                        x.for_each(landCount, SubtreeCopyK{order.p, cA, cB});
-                        x.for_each(landCount, SubtreeRoundK{order.p, jA, jB, cA, cB});
-                        std::swap(jA, jB); std::swap(cA, cB);
+#if PB_CUDA
+                    if (subtreeGrid < 0) {
+                        int perSm = 0, dev = 0, coop = 0;
+                        PB_CUDA_CHECK(cudaGetDevice(&dev));
+                        PB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+                        PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_subtree_counts, 256, 0));
+                        subtreeGrid = (coop && perSm > 0) ? x.sm_count * std::min(perSm, 2) : 0;
                     }
-                    x.for_each(landCount, SubtreeWordsK{order.p, cA, words.p});
+                    if (subtreeGrid > 0) {
+                        const int* po = order.p; const int* pp = pos.p; const int* pt = drainTarget.p; const uint8_t* pi = isOcean;
+                        int nn = landCount; unsigned long long* pw = words.p; int* pa = counters.p + 14;
+                        void* args[] = {&po, &pp, &pt, &pi, &jA, &jB, &cA, &cB, &nn, &pw, &pa};
+                        launch_stats().launches++;
+                        ProfScope ps(x.prof, "pb::k_subtree_counts", x.stream);
+                        PB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_subtree_counts, dim3(subtreeGrid), dim3(256), args, 0, x.stream));
+                    } else
+#endif
+                    {
+                        x.for_each(landCount, SubtreeInitK{order.p, pos.p, drainTarget.p, isOcean, jA, cA});
+                        int rounds = 1; while ((1ll << rounds) < (long long)landCount + 1) rounds++;
+                        for (int k = 0; k < rounds; k++) {
+                            x.for_each(landCount, SubtreeCopyK{order.p, cA, cB});
+                            x.for_each(landCount, SubtreeRoundK{order.p, jA, jB, cA, cB});
+                            std::swap(jA, jB); std::swap(cA, cB);
+                        }
+                        x.for_each(landCount, SubtreeWordsK{order.p, cA, words.p});
+                    }
                 } else {
                     dev_memset(words.p, 0, sizeof(unsigned long long) * (size_t)N, x.stream);
                     x.ordered(landCount, AccumulateK{g, order.p, pos.p, drainTarget.p, isOcean, nullptr, words.p});

@@ -120,6 +120,43 @@ struct SubtreeWordsK {
     PB_DEV void operator()(int i) const { const int r = order[i]; contrib[r] = make_word((float)cnt[r], 1); }
 };
 
+#if PB_CUDA
+}  // namespace pb
+#include <cooperative_groups.h>
+namespace pb {
+// all doubling rounds in one cooperative launch (one CTA per SM, two grid barriers per round) — the rounds stop as soon as no
+// jump pointer is left, i.e. after ⌈log2(deepest early-edge chain)⌉ rounds instead of ⌈log2(land)⌉ launches pairs
+__global__ void __launch_bounds__(256) k_subtree_counts(const int* order, const int* pos, const int* target, const uint8_t* isOcean,
+                                                        int* jA, int* jB, int* cA, int* cB, int n, unsigned long long* contrib, int* active) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    SubtreeInitK init{order, pos, target, isOcean, jA, cA};
+    for (int i = gtid; i < n; i += stride) init(i);
+    if (gtid == 0) { active[0] = 0; active[1] = 0; }
+    grid.sync();
+    for (int k = 0; k < 31; k++) {
+        for (int i = gtid; i < n; i += stride) { const int r = order[i]; cB[r] = __ldcg(cA + r); }
+        grid.sync();
+        int mine = 0;
+        for (int i = gtid; i < n; i += stride) {
+            const int r = order[i];
+            const int j = __ldcg(jA + r);
+            int jj = -1;
+            if (j >= 0) { atomicAdd(cB + j, __ldcg(cA + r)); jj = __ldcg(jA + j); mine |= jj >= 0; }
+            jB[r] = jj;
+        }
+        if (mine) atomicOr(active + (k & 1), 1);
+        if (gtid == 0) active[(k + 1) & 1] = 0;
+        grid.sync();
+        int* t = jA; jA = jB; jB = t;
+        t = cA; cA = cB; cB = t;
+        if (!*(volatile int*)(active + (k & 1))) break;
+    }
+    for (int i = gtid; i < n; i += stride) { const int r = order[i]; contrib[r] = make_word((float)__ldcg(cA + r), 1); }
+}
+#endif
+
 // final value: init + every donor's contribution in position order; also the donor count (mod 256)
 struct AccumulateFinalK {
     Csr g; const int* pos; const int* target; const uint8_t* isOcean; const float* initv;
