@@ -14,7 +14,7 @@
 
 namespace pb {
 
-#define PB_SPIN 32   // polls per try_run before the lane yields to the retry loop
+#define PB_SPIN 4    // polls per try_run before the lane yields to the retry loop (which backs off, pb_platform.h)
 
 struct LandFlagK { const uint8_t* isOcean; uint8_t* flag; PB_DEV void operator()(int r) const { flag[r] = isOcean[r] ? 0 : 1; } };
 struct FillIntK { int* p; int v; PB_DEV void operator()(int i) const { p[i] = v; } };

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 150 python bench.py --workload climate --cells 10000000 --steps 2 --warmup 1 --no-cpu > gpurun_out/ab_packed.json 2> gpurun_out/ab_packed.log; echo "rc=$?" >> gpurun_out/ab_packed.log
-PB_NO_PACKED_ROWS=1 timeout 150 python bench.py --workload climate --cells 10000000 --steps 2 --warmup 1 --no-cpu > gpurun_out/ab_csr.json 2> gpurun_out/ab_csr.log; echo "rc=$?" >> gpurun_out/ab_csr.log
-grep -A12 "per-kernel device time" gpurun_out/ab_packed.log | head -14; grep -A12 "per-kernel device time" gpurun_out/ab_csr.log | head -14
+timeout 120 python -m pytest tests/test_terrain_post_parity.py tests/test_large_parity.py -m gpu -x -q > gpurun_out/diag_tests.log 2>&1; echo "rc=$?" >> gpurun_out/diag_tests.log
+timeout 150 python bench.py --workload post --steps 3 --warmup 2 --no-cpu --in-flight 0 > gpurun_out/diag_post.json 2> gpurun_out/diag_post.log; echo "rc=$?" >> gpurun_out/diag_post.log
+tail -3 gpurun_out/diag_tests.log; grep -A8 "per-kernel device time" gpurun_out/diag_post.log; head -c 200 gpurun_out/diag_post.json
