@@ -1007,6 +1007,57 @@ struct ShadowSweepK {
         finish(r, s, val, w);
     }
 };
+// The same sweep over a COMPACTED list of the land rows.  Fibonacci ids advance by the golden angle in longitude, so land and
+// ocean rows alternate pseudo-randomly in id order: the row-indexed kernel above pulls in almost every cache line of the
+// offsets, packed rows and edge weights although only the land rows (≈ 27 %) use them — 500 MB of DRAM traffic per sweep at
+// 10M cells for 262 MB of algorithmic bytes (profiles/r02_sweeps_ncu.md).  The reference compacts its land edge lists for the
+// same reason (js/precipitation.js:520-547).  Here every land row owns one contiguous 48-byte record — its packed neighbour
+// word and eight edge weights — and ocean rows are never visited: both ping-pong buffers start as the initial field, and an
+// ocean cell keeps that value through the whole propagation.
+// any row functor over a compacted row list: the lanes of a warp all carry work (rows outside the list keep their value in
+// both ping-pong buffers)
+template <class F>
+struct OverRowsK { const int* rows; F f; PB_DEV void operator()(int i) const { f(rows[i]); } };
+struct LandPackK { const int* landRow; const PackedRow* pack; PackedRow* out; PB_DEV void operator()(int i) const { out[i] = pack[landRow[i]]; } };
+struct LandWeightsK {
+    Csr g; const int* landRow; const float* wt; float* out;
+    PB_DEV void operator()(int i) const {
+        const int r = landRow[i];
+        const int b = g.off[r], deg = g.off[r + 1] - b;
+        for (int k = 0; k < PB_ROW_FAST; k++) out[(size_t)PB_ROW_FAST * i + k] = k < deg ? wt[b + k] : 0.0f;
+    }
+};
+struct ShadowLandK {
+    Csr g; const int* landRow; const PackedRow* landPack; const float* landWt; const float* wtCsr; const uint8_t* isLand;
+    const float* src; float* dst; double keepFactor; int sign;
+    PB_DEV void operator()(int i) const {
+        const int r = landRow[i];
+        RowIds row; int deg;
+        if (!row.load_word(landPack + i, r, deg)) {       // escape row: the CSR form
+            const int b = g.off[r];
+            ShadowSweepK{g, isLand, wtCsr, src, dst, keepFactor, sign}.row(r, b, g.off[r + 1] - b, g.adj + b);
+            return;
+        }
+        const float s = src[r];
+        float wk[PB_ROW_FAST], v[PB_ROW_FAST];
+#if PB_CUDA
+        const float4 w0 = __ldg((const float4*)(landWt + (size_t)PB_ROW_FAST * i)), w1 = __ldg((const float4*)(landWt + (size_t)PB_ROW_FAST * i) + 1);
+        wk[0] = w0.x; wk[1] = w0.y; wk[2] = w0.z; wk[3] = w0.w; wk[4] = w1.x; wk[5] = w1.y; wk[6] = w1.z; wk[7] = w1.w;
+#else
+        for (int k = 0; k < PB_ROW_FAST; k++) wk[k] = landWt[(size_t)PB_ROW_FAST * i + k];
+#endif
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++) v[k] = src[row.nb[k]];
+        double val = 0, w = 0;
+#pragma unroll
+        for (int k = 0; k < PB_ROW_FAST; k++)
+            if (wk[k] > 0) {
+                const double vv = v[k];
+                if (sign < 0 ? (vv < 0) : (vv > 0)) { val += vv * (double)wk[k]; w += (double)wk[k]; }
+            }
+        ShadowSweepK{g, isLand, wtCsr, src, dst, keepFactor, sign}.finish(r, s, val, w);
+    }
+};
 struct KeepExtremeK {   // :572-574 / :599-601
     const float* src; float* field; int sign;
     PB_DEV void operator()(int r) const { if (sign < 0 ? (src[r] < field[r]) : (src[r] > field[r])) field[r] = src[r]; }

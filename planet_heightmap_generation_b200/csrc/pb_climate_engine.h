@@ -28,6 +28,7 @@ struct Climate {
     DevBuf<uint8_t> plateTable, contPlate, flagA, flagB, flagC, noiseTab;
     DevBuf<double> samples, scalars;
     DevBuf<SplineDev> splines;
+    DevBuf<int> landRow; DevBuf<PackedRow> landPack; DevBuf<float> landWt; int nLand = 0;
 
     explicit Climate(Mesh* mesh) : m(mesh), N(mesh->N) {}
 
@@ -266,6 +267,14 @@ struct Climate {
         const double shadowDecay = 1 - pb_pow(0.15, 1.0 / shadowHops);
         const double windwardDecay = 1 - pb_pow(0.25, 1.0 / windwardHops);
 
+        // compacted land rows for the rain-shadow / windward propagation (one 16-byte packed word + eight weights per land row)
+        const bool landOk = g.pack != nullptr && !getenv("PB_NO_LAND_COMPACT");
+        if (landOk) {
+            cnt.ensure(160);
+            m->prims.compact_flagged(x, isLand, N, landRow.ensure(N), cnt.p + 152);
+            nLand = m->read_int(cnt.p + 152);
+            if (nLand > 0) x.for_each(nLand, LandPackK{landRow.p, g.pack, landPack.ensure(nLand)});
+        }
         for (int s = 0; s < 2; s++) {
             const std::string name = s == 0 ? "summer" : "winter";
             const float* itczLats = cF(s == 0 ? "itczLatsSummer" : "itczLatsWinter");
@@ -278,9 +287,14 @@ struct Climate {
             x.for_each(N, MoistureInitK{g, m->xyz.p, isLand, coastDistLand, cF("r_ocean_warmth_" + name), wX, wY, wZ, src});
             {
                 const float* xyzp = m->xyz.p;
-                sweep_loop(*m, src, maxHops, bufB, [=](const float* in, float* out) {
-                    return AdvectK{g, xyzp, isLand, windE, windN, wX, wY, wZ, heightKm, in, out, depletionBase, maxHops};
-                });
+                auto make = [=](const float* in, float* out) { return AdvectK{g, xyzp, isLand, windE, windN, wX, wY, wZ, heightKm, in, out, depletionBase, maxHops}; };
+                if (landOk && nLand > 0 && !sweeps_sharded(*m)) {
+                    // ocean cells keep their initial moisture (:122): only the land rows are swept, 32 working lanes per warp
+                    dev_copy(bufB, src, sizeof(float) * (size_t)N, 2, x.stream);
+                    const int* lr = landRow.p;
+                    sweep_loop_items(*m, nLand, src, maxHops, bufB, [=](const float* in, float* out) { return OverRowsK<AdvectK>{lr, make(in, out)}; });
+                } else
+                    sweep_loop(*m, src, maxHops, bufB, make);
             }
             float* precip = F("r_precip_complex_" + name);
             float* rainShadow = F("r_rainshadow_" + name);
@@ -293,17 +307,21 @@ struct Climate {
             float* ping = conv; float* pong = m->tmp.ensure(N);            // nor is the convergence field
             dev_copy(shadowField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
             dev_copy(windwardField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-            {
-                const float* wt = upWt.p; const double keep = 1 - shadowDecay;
+            const bool compact = landOk && !sweeps_sharded(*m);      // land-compacted records (pb_climate.h: ShadowLandK)
+            for (int dir = 0; dir < 2; dir++) {
+                const float* wt = dir == 0 ? upWt.p : dnWt.p;
+                const double keep = dir == 0 ? 1 - shadowDecay : 1 - windwardDecay;
+                const int sign = dir == 0 ? -1 : +1, hops = dir == 0 ? shadowHops : windwardHops;
                 dev_copy(ping, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                sweep_loop(*m, ping, shadowHops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, -1}; });
-                x.for_each(N, KeepExtremeK{ping, shadowField, -1});
-            }
-            {
-                const float* wt = dnWt.p; const double keep = 1 - windwardDecay;
-                dev_copy(ping, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-                sweep_loop(*m, ping, windwardHops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, +1}; });
-                x.for_each(N, KeepExtremeK{ping, windwardField, +1});
+                if (compact) {
+                    dev_copy(pong, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);     // ocean rows are never written: both buffers hold them
+                    float* lw = landWt.ensure((size_t)PB_ROW_FAST * nLand);
+                    x.for_each(nLand, LandWeightsK{g, landRow.p, wt, lw});
+                    const int* lr = landRow.p; const PackedRow* lp = landPack.p;
+                    sweep_loop_items(*m, nLand, ping, hops, pong, [=](const float* in, float* out) { return ShadowLandK{g, lr, lp, lw, wt, isLand, in, out, keep, sign}; });
+                } else
+                    sweep_loop(*m, ping, hops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, sign}; });
+                x.for_each(N, KeepExtremeK{ping, dir == 0 ? shadowField : windwardField, sign});
             }
             x.for_each(N, MergeShadowK{shadowField, windwardField, rainShadow});
             m->smooth_field(rainShadow, rsSmoothPasses);

@@ -301,6 +301,19 @@ void sweep_loop(Mesh& m, float* field, int passes, float* scratch, const Make& m
     }
     if (src != field) dev_copy(field, src, sizeof(float) * (size_t)m.N, 2, m.ex().stream);
 }
+inline bool sweeps_sharded(const Mesh& m) { return m.shards && m.shards->active(); }
+// unsharded loop over a compacted item list (`count` items per sweep); scratch must already hold the values of the cells the
+// items never write
+template <class Make>
+void sweep_loop_items(Mesh& m, int count, float* field, int passes, float* scratch, const Make& make) {
+    if (passes <= 0) return;
+    float* src = field; float* dst = scratch;
+    for (int p = 0; p < passes; p++) {
+        m.ex().for_each(count, make((const float*)src, dst));
+        std::swap(src, dst);
+    }
+    if (src != field) dev_copy(field, src, sizeof(float) * (size_t)m.N, 2, m.ex().stream);
+}
 inline void smooth_field_impl(Mesh& m, float* field, int passes) {
     const Csr g = m.csr();
     sweep_loop(m, field, passes, m.tmp.ensure(m.N), [g](const float* src, float* dst) { return SmoothFieldK{g, src, dst}; });

@@ -71,12 +71,14 @@ struct RowIds {
         for (int k = 0; k < PB_ROW_FAST; k++) nb[k] = k < deg ? ids[k] : r;
     }
     // whole row from the packed word; false: escape row (take the CSR path)
-    PB_DEV bool load_packed(const PackedRow* pack, int r, int& deg) {
+    PB_DEV bool load_packed(const PackedRow* pack, int r, int& deg) { return load_word(pack + r, r, deg); }
+    // the packed word of row r stored at `word` (compacted row lists keep their own array of words)
+    PB_DEV bool load_word(const PackedRow* word, int r, int& deg) {
 #if PB_CUDA
-        const uint4 q = __ldg((const uint4*)(pack + r));
+        const uint4 q = __ldg((const uint4*)word);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #else
-        const uint32_t* w = pack[r].w;
+        const uint32_t* w = word->w;
 #endif
         if ((w[0] & 0xffffu) == PB_PACK_ESCAPE) return false;
         int n = 0;
