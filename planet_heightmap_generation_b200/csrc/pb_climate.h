@@ -298,28 +298,38 @@ struct BfsLevelK {
 }  // namespace pb
 #include <cooperative_groups.h>
 namespace pb {
-// All levels of one BFS in a single cooperative launch: one grid-wide barrier per level instead of one kernel
-// launch per level (a BFS at 1M cells has 100–300 levels of a few thousand cells each — launch-latency bound).
-__global__ void __launch_bounds__(256) k_bfs_persistent(Csr g, const uint8_t* passable, int* dist, int* frontA, int* frontB, int* cnt) {
+// All levels of up to three independent BFS in a single cooperative launch: one grid-wide barrier per level for all of them
+// together instead of one kernel launch per level and BFS (a BFS at 1M cells has 100–300 levels of a few thousand cells each —
+// barrier-latency bound, so the two BFS of computeWind and the three of computeOceanCurrents each share their barriers).
+struct BfsMulti { int k; const uint8_t* passable[3]; int* dist[3]; int* fa[3]; int* fb[3]; int* cnt[3]; };
+__global__ void __launch_bounds__(256) k_bfs_persistent(Csr g, BfsMulti B) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    int* cur = frontA; int* nxt = frontB;
     for (int level = 0;; level++) {
-        const int n = ld_volatile(cnt + level % 3);
-        if (n == 0) break;
-        if (gtid == 0) cnt[(level + 2) % 3] = 0;
-        const int d = level + 1;
-        int* slot = cnt + (level + 1) % 3;
-        for (int i = gtid; i < n; i += stride) {
-            const int r = __ldcg(cur + i);      // written by other SMs in the previous level: read through L2
-            for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) {
-                const int nb = g.adj[j];
-                if (passable[nb] && ld_volatile(dist + nb) == -1 && atomicCAS(dist + nb, -1, d) == -1) nxt[atomicAdd(slot, 1)] = nb;
+        bool any = false;
+        for (int b = 0; b < B.k; b++) {
+            int* cnt = B.cnt[b];
+            const int n = ld_volatile(cnt + level % 3);
+            if (gtid == 0) cnt[(level + 2) % 3] = 0;
+            if (n == 0) continue;
+            any = true;
+            const int d = level + 1;
+            int* slot = cnt + (level + 1) % 3;
+            const int* cur = (level & 1) ? B.fb[b] : B.fa[b];
+            int* nxt = (level & 1) ? B.fa[b] : B.fb[b];
+            const uint8_t* passable = B.passable[b];
+            int* dist = B.dist[b];
+            for (int i = gtid; i < n; i += stride) {
+                const int r = __ldcg(cur + i);      // written by other SMs in the previous level: read through L2
+                for (int j = g.off[r], e = g.off[r + 1]; j < e; j++) {
+                    const int nb = g.adj[j];
+                    if (passable[nb] && ld_volatile(dist + nb) == -1 && atomicCAS(dist + nb, -1, d) == -1) nxt[atomicAdd(slot, 1)] = nb;
+                }
             }
         }
+        if (!any) break;
         grid.sync();
-        int* t = cur; cur = nxt; nxt = t;
     }
 }
 #endif

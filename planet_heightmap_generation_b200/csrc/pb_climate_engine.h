@@ -50,12 +50,17 @@ struct Climate {
         sweep_loop(*m, field, passes, m->tmp.ensure(N), [=](const float* src, float* dst) { return SmoothMaskedK{g, mask, src, dst, z}; });
     }
 
-    // hop counts from the cells flagged in seedFlag (their dist is already 0, everything else -1)
-    void bfs(int* dist, const uint8_t* passable, const uint8_t* seedFlag) {
+    // hop counts from the cells flagged in seedFlag (their dist is already 0, everything else -1) for up to three independent
+    // BFS at once
+    DevBuf<int> bfsFront[3][2], bfsCnt;
+    void bfs_many(int k, int* const* dist, const uint8_t* const* passable, const uint8_t* const* seedFlag) {
         const Exec& x = ex();
-        cnt.ensure(160); frontA.ensure(N); frontB.ensure(N);
-        dev_memset(cnt.p, 0, 4 * sizeof(int), x.stream);
-        m->prims.compact_flagged(x, seedFlag, N, frontA.p, cnt.p + 0);
+        bfsCnt.ensure(12);
+        dev_memset(bfsCnt.p, 0, 12 * sizeof(int), x.stream);
+        for (int b = 0; b < k; b++) {
+            bfsFront[b][0].ensure(N); bfsFront[b][1].ensure(N);
+            m->prims.compact_flagged(x, seedFlag[b], N, bfsFront[b][0].p, bfsCnt.p + 4 * b);
+        }
 #if PB_CUDA
         if (bfsGrid < 0) {
             int perSm = 0, dev = 0, coop = 0;
@@ -66,28 +71,33 @@ struct Climate {
         }
         if (bfsGrid > 0) {
             Csr g = csr();
-            int* fa = frontA.p; int* fb = frontB.p; int* c = cnt.p;
-            void* args[] = {&g, (void*)&passable, &dist, &fa, &fb, &c};
+            BfsMulti B{};
+            B.k = k;
+            for (int b = 0; b < k; b++) { B.passable[b] = passable[b]; B.dist[b] = dist[b]; B.fa[b] = bfsFront[b][0].p; B.fb[b] = bfsFront[b][1].p; B.cnt[b] = bfsCnt.p + 4 * b; }
+            void* args[] = {&g, &B};
             launch_stats().launches++;
             ProfScope ps(x.prof, "pb::k_bfs_persistent", x.stream);
             PB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_persistent, dim3(bfsGrid), dim3(256), args, 0, x.stream));
             return;
         }
 #endif
-        int* cur = frontA.p; int* nxt = frontB.p;
-        const int CHECK = 16;
-        for (int level = 0;; level++) {
-            x.for_each_dev(cnt.p + level % 3, BfsLevelK{csr(), passable, dist, cur, nxt, cnt.p, level});
-            std::swap(cur, nxt);
-            if ((level + 1) % CHECK == 0) {
-                int h[3];
-                dev_copy(h, cnt.p, sizeof h, 1, x.stream);
-                stream_sync(x.stream);
-                if (h[(level + 1) % 3] == 0) break;
+        for (int b = 0; b < k; b++) {
+            int* cur = bfsFront[b][0].p; int* nxt = bfsFront[b][1].p; int* c = bfsCnt.p + 4 * b;
+            const int CHECK = 16;
+            for (int level = 0;; level++) {
+                x.for_each_dev(c + level % 3, BfsLevelK{csr(), passable[b], dist[b], cur, nxt, c, level});
+                std::swap(cur, nxt);
+                if ((level + 1) % CHECK == 0) {
+                    int h[3];
+                    dev_copy(h, c, sizeof h, 1, x.stream);
+                    stream_sync(x.stream);
+                    if (h[(level + 1) % 3] == 0) break;
+                }
+                if (level > N) throw Error("bfs did not terminate");
             }
-            if (level > N) throw Error("bfs did not terminate");
         }
     }
+    void bfs(int* dist, const uint8_t* passable, const uint8_t* seedFlag) { bfs_many(1, &dist, &passable, &seedFlag); }
 
     // *out = percentile of the values whose order-preserving keys are in keys[0..n) (keys are consumed)
     void percentile(uint32_t* k, int n, const int* nDev, double p, double* out) {
@@ -138,15 +148,10 @@ struct Climate {
         dev_memset(m->best.p, 0, sizeof(unsigned long long), x.stream);
         x.for_each(N, CcBestK{isOcean, m->parent.p, m->ccSize.p, m->best.p});
         int* coastDist = I("r_coastDistLand");
-        flagA.ensure(N);
+        flagA.ensure(N); flagB.ensure(N);
         x.for_each(N, LandCoastSeedK{g, isLand, isOcean, m->parent.p, m->best.p, coastDist, flagA.p});
-        bfs(coastDist, isLand, flagA.p);
-        float* cont = F("r_continentality");
-        x.for_each(N, ContinentalityK{isLand, coastDist, cont, aek});
-        const int contSmoothPasses = std::max(1, js_round_i(100 / aek));
-        m->smooth_field(cont, contSmoothPasses);
 
-        // plate-based continentality (:556-593)
+        // plate-based continentality (:556-593): its BFS shares the launch (and the grid barriers) with the coast BFS
         int maxId = 0;
         for (int k = 0; k < nIds; k++) { if (plateIsOceanIdsHost[k] < 0) throw std::invalid_argument("negative plate id"); maxId = std::max(maxId, plateIsOceanIdsHost[k]); }
         const int tableSize = maxId + 1;
@@ -159,8 +164,17 @@ struct Climate {
         contPlate.ensure(N);
         x.for_each(N, ContPlateK{r_plate, plateTable.p, tableSize, contPlate.p});
         int* plateDist = I("r_plateDist");
-        x.for_each(N, MaskBoundarySeedK{g, contPlate.p, plateDist, flagA.p});
-        bfs(plateDist, contPlate.p, flagA.p);
+        x.for_each(N, MaskBoundarySeedK{g, contPlate.p, plateDist, flagB.p});
+        {
+            int* dists[2] = {coastDist, plateDist};
+            const uint8_t* pass[2] = {isLand, contPlate.p};
+            const uint8_t* seedsF[2] = {flagA.p, flagB.p};
+            bfs_many(2, dists, pass, seedsF);
+        }
+        float* cont = F("r_continentality");
+        x.for_each(N, ContinentalityK{isLand, coastDist, cont, aek});
+        const int contSmoothPasses = std::max(1, js_round_i(100 / aek));
+        m->smooth_field(cont, contSmoothPasses);
         float* pcont = F("r_plateContinentality");
         x.for_each(N, ContinentalityK{contPlate.p, plateDist, pcont, aek});
         m->smooth_field(pcont, contSmoothPasses);
@@ -197,9 +211,12 @@ struct Climate {
         int *coast = I("r_oceanCoastDist"), *west = I("r_westCoastDist"), *east = I("r_eastCoastDist");
         flagA.ensure(N); flagB.ensure(N); flagC.ensure(N);
         x.for_each(N, OceanCoastSeedK{g, m->xyz.p, isOcean, cF("r_eastX"), cF("r_eastY"), cF("r_eastZ"), coast, west, east, flagA.p, flagB.p, flagC.p});
-        bfs(coast, isOcean, flagA.p);
-        bfs(west, isOcean, flagB.p);
-        bfs(east, isOcean, flagC.p);
+        {
+            int* dists[3] = {coast, west, east};
+            const uint8_t* pass[3] = {isOcean, isOcean, isOcean};
+            const uint8_t* seedsF[3] = {flagA.p, flagB.p, flagC.p};
+            bfs_many(3, dists, pass, seedsF);
+        }
         cnt.ensure(160);
         int* bins = cnt.p + 4; int* circ = cnt.p + 148; int* oceanCount = cnt.p + 150;
         dev_memset(bins, 0, sizeof(int) * 148, x.stream);
