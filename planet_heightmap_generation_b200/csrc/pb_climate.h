@@ -1024,10 +1024,6 @@ struct ShadowSweepK {
 // same reason (js/precipitation.js:520-547).  Here every land row owns one contiguous 48-byte record — its packed neighbour
 // word and eight edge weights — and ocean rows are never visited: both ping-pong buffers start as the initial field, and an
 // ocean cell keeps that value through the whole propagation.
-// any row functor over a compacted row list: the lanes of a warp all carry work (rows outside the list keep their value in
-// both ping-pong buffers)
-template <class F>
-struct OverRowsK { const int* rows; F f; PB_DEV void operator()(int i) const { f(rows[i]); } };
 struct LandPackK { const int* landRow; const PackedRow* pack; PackedRow* out; PB_DEV void operator()(int i) const { out[i] = pack[landRow[i]]; } };
 struct LandWeightsK {
     Csr g; const int* landRow; const float* wt; float* out;

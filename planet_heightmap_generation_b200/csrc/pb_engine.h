@@ -269,6 +269,7 @@ struct Mesh {
     DevBuf<int> liftUp, liftDepthA, liftDepthB;
     int floodSmemMax = -1;
     int subtreeGrid = -1;
+    DevBuf<int> subtreeExtra;
     int lastMaxHeap = 0;
     void flood_heap_cuda(const float* elev) {
         const Exec& x = ex();
@@ -464,12 +465,13 @@ struct Mesh {
                         PB_CUDA_CHECK(cudaGetDevice(&dev));
                         PB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
                         PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_subtree_counts, 256, 0));
-                        subtreeGrid = (coop && perSm > 0) ? x.sm_count * std::min(perSm, 2) : 0;
+                        subtreeGrid = (coop && perSm > 0) ? x.sm_count : 0;
                     }
                     if (subtreeGrid > 0) {
                         const int* po = order.p; const int* pp = pos.p; const int* pt = drainTarget.p; const uint8_t* pi = isOcean;
                         int nn = landCount; unsigned long long* pw = words.p; int* pa = counters.p + 14;
-                        void* args[] = {&po, &pp, &pt, &pi, &jA, &jB, &cA, &cB, &nn, &pw, &pa};
+                        int* dC = subtreeExtra.ensure(N);
+                        void* args[] = {&po, &pp, &pt, &pi, &jA, &jB, &cA, &cB, &dC, &nn, &pw, &pa};
                         launch_stats().launches++;
                         ProfScope ps(x.prof, "pb::k_subtree_counts", x.stream);
                         PB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_subtree_counts, dim3(subtreeGrid), dim3(256), args, 0, x.stream));
@@ -498,7 +500,7 @@ struct Mesh {
                         dev_copy(taps->landOrder, order.p, sizeof(int) * (size_t)landCount, 2, x.stream);
                     }
                 }
-                x.for_each(N, SolvePrepK{g, pos.p, drainTarget.p, isOcean, k0.p, k1.p, k2.p});
+                x.for_each(landCount, OverRowsK<SolvePrepK>{order.p, SolvePrepK{g, pos.p, drainTarget.p, isOcean, k0.p, k1.p, k2.p}});   // land rows only
                 x.for_each(N, PackElevK{elev, words.p});
                 x.ordered(landCount, SolveK{order.p, landCount, drainTarget.p, isOcean, cellDist.p, flow.p, elev, words.p,
                                             k0.p, k1.p, k2.p, K, m, dt});

@@ -124,36 +124,42 @@ struct SubtreeWordsK {
 }  // namespace pb
 #include <cooperative_groups.h>
 namespace pb {
-// all doubling rounds in one cooperative launch (one CTA per SM, two grid barriers per round) — the rounds stop as soon as no
-// jump pointer is left, i.e. after ⌈log2(deepest early-edge chain)⌉ rounds instead of ⌈log2(land)⌉ launches pairs
+// all doubling rounds in one cooperative launch (one CTA per SM) with ONE grid barrier per round: a cell folds the additions
+// it received in the previous round (dPrev) into its own count, zeroes that slot for reuse, and hands the folded count to its
+// current jump target's slot of the other buffer (dCur).  The rounds stop after the first one in which nobody had a jump
+// target left, i.e. after ⌈log2(deepest early-edge chain)⌉ + 1 rounds.
 __global__ void __launch_bounds__(256) k_subtree_counts(const int* order, const int* pos, const int* target, const uint8_t* isOcean,
-                                                        int* jA, int* jB, int* cA, int* cB, int n, unsigned long long* contrib, int* active) {
+                                                        int* jA, int* jB, int* cnt, int* dPrev, int* dCur, int n, unsigned long long* contrib, int* active) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    SubtreeInitK init{order, pos, target, isOcean, jA, cA};
-    for (int i = gtid; i < n; i += stride) init(i);
+    for (int i = gtid; i < n; i += stride) {
+        const int r = order[i];
+        const int t = target[r];
+        jA[r] = (t >= 0 && !isOcean[t] && pos[t] > i) ? t : -1;
+        cnt[r] = 1; dPrev[r] = 0; dCur[r] = 0;
+    }
     if (gtid == 0) { active[0] = 0; active[1] = 0; }
     grid.sync();
-    for (int k = 0; k < 31; k++) {
-        for (int i = gtid; i < n; i += stride) { const int r = order[i]; cB[r] = __ldcg(cA + r); }
-        grid.sync();
+    for (int k = 0; k < 40; k++) {
         int mine = 0;
         for (int i = gtid; i < n; i += stride) {
             const int r = order[i];
+            const int s = cnt[r] + __ldcg(dPrev + r);
+            cnt[r] = s; dPrev[r] = 0;
             const int j = __ldcg(jA + r);
             int jj = -1;
-            if (j >= 0) { atomicAdd(cB + j, __ldcg(cA + r)); jj = __ldcg(jA + j); mine |= jj >= 0; }
+            if (j >= 0) { atomicAdd(dCur + j, s); jj = __ldcg(jA + j); mine = 1; }
             jB[r] = jj;
         }
         if (mine) atomicOr(active + (k & 1), 1);
         if (gtid == 0) active[(k + 1) & 1] = 0;
         grid.sync();
         int* t = jA; jA = jB; jB = t;
-        t = cA; cA = cB; cB = t;
+        t = dPrev; dPrev = dCur; dCur = t;
         if (!*(volatile int*)(active + (k & 1))) break;
     }
-    for (int i = gtid; i < n; i += stride) { const int r = order[i]; contrib[r] = make_word((float)__ldcg(cA + r), 1); }
+    for (int i = gtid; i < n; i += stride) { const int r = order[i]; contrib[r] = make_word((float)cnt[r], 1); }
 }
 #endif
 

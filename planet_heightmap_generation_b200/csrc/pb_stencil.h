@@ -122,6 +122,10 @@ struct SmoothFieldK {
     }
 };
 
+// any row functor over a compacted row list: the lanes of a warp all carry work (rows outside the list are not visited)
+template <class F>
+struct OverRowsK { const int* rows; F f; PB_DEV void operator()(int i) const { f(rows[i]); } };
+
 // js/planet-worker.js:51-54
 struct IsOceanK {
     const float* elev; uint8_t* isOcean;
