@@ -477,7 +477,8 @@ def pipelined_throughput(args, mesh, xyz, local, planets: int, steps: int):
 # cell-range sharded sweep loops: strong scaling of ONE planet's climate stack across the ranks
 # ---------------------------------------------------------------------------------------------------
 def build_eroded_planet(dm, cells, hiters):
-    """(elev, pio, r_plate) of the seeded planet on `dm`: plates → assignElevation → runPostProcessing, all on the device"""
+    """(elev, pio, r_plate) of the seeded planet on `dm`: plates → assignElevation (→ runPostProcessing when hiters >= 0), all on
+    the device"""
     import torch
     from planet_heightmap_generation_b200 import plates as pl
     from planet_heightmap_generation_b200.elevation import assignElevation
@@ -494,7 +495,8 @@ def build_eroded_planet(dm, cells, hiters):
     sp = pl.buildSuperPlates(dm, r_plate, seeds, vec, pio, dens, out=r_super)
     res = assignElevation(dm, None, pio, r_plate, vec, seeds, SEED, NMAG, SEED, SPREAD, dens, sp)
     elev = res["r_elevation"]
-    runPostProcessing(dm, None, elev, SLIDERS, None, SEED, res["debugLayers"]["hotspot"], hItersOverride=hiters, timing=False)
+    if hiters >= 0:
+        runPostProcessing(dm, None, elev, SLIDERS, None, SEED, res["debugLayers"]["hotspot"], hItersOverride=hiters, timing=False)
     return elev, pio, r_plate
 
 
@@ -513,7 +515,7 @@ def sharded_climate_probe(args, rank, world, local, cells, steps=2):
     N = cells + 1
     group = SweepShardGroup(dm, rank, world, min_cells=0)
     group.set_min_cells(1 << 62)                       # the planet itself is built unsharded
-    elev, pio, r_plate = build_eroded_planet(dm, cells, 10)
+    elev, pio, r_plate = build_eroded_planet(dm, cells, -1)    # climate of the pre-erosion elevation: the probe times sweeps, not erosion
     koppen = torch.empty(N, dtype=torch.uint8, device=dev)
     setup_s = time.perf_counter() - t_setup
 
@@ -873,9 +875,34 @@ def run_b200(args):
                              "against one pass of oracle/ on the same (N, seed, sliders)"}
         log(f"[bench] parity vs oracle at {N} cells: {parity['mismatches']} mismatching cells over {len(fields)} arrays")
 
+    # ---- the main line is complete here; the supplementary legs below run under a watchdog ----------------------------
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if shards_mode else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "impl": "b200", "config": bench_config(args, world), "land_cells": land, "parity": parity,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
+                "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
+        "cpu_baseline": cpu_baseline, "sharded_sweeps": None, "throughput_in_flight": None, "kernel_breakdown": breakdown, "library": dm.lib.version,
+    }
+    import threading
+
+    def give_up():
+        # a supplementary leg did not come back (e.g. a peer rank died): the measured line still goes out, every rank leaves
+        if rank == 0:
+            line["supplementary"] = f"a supplementary leg did not finish within {args.extras_timeout} s and was abandoned"
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    watchdog = threading.Timer(args.extras_timeout, give_up)
+    watchdog.daemon = True
+    watchdog.start()
+
     # ---- several planets in flight (supplementary: `value` above is one planet at a time) ----------------------
     in_flight = None
-    if wl == "full" and args.in_flight > 1 and not shards_mode:
+    if wl == "full" and args.in_flight > 1 and world == 1:
         secs, agree, ref = pipelined_throughput(args, mesh, xyz, local, args.in_flight, args.steps)
         if world > 1:
             t = torch.tensor([secs], dtype=torch.float64, device=dev)
@@ -886,6 +913,8 @@ def run_b200(args):
                      "matches_single_planet_path": bool(agree and (ref[0] == elev_dev_final).all().item() and (ref[1] == koppen).all().item()),
                      "note": "one pb_context + CUDA stream + host thread per planet, same full pipeline per planet; host wall clock "
                              "around device synchronizes"}
+
+    line["throughput_in_flight"] = in_flight
 
     # ---- the data path that shards: sweep loops by cell-id range (pb_shardsweep.h) -------------------------------
     sharding = None
@@ -913,18 +942,11 @@ def run_b200(args):
     elif world > 1 and args.shard_probe_cells > 0 and wl == "full":
         sharding = sharded_climate_probe(args, rank, world, local, args.shard_probe_cells)
 
+    line["sharded_sweeps"] = sharding
+    watchdog.cancel()
+
     if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if shards_mode else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "impl": "b200", "config": bench_config(args, world), "land_cells": land, "parity": parity,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000 * e2e_s / args.steps,
-                    "matches_device_path": same, "stages_last_step_ms": {k: round(v, 2) for k, v in host_stage.items()}},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_sweep": roofline_sweep,
-            "cpu_baseline": cpu_baseline, "sharded_sweeps": sharding, "throughput_in_flight": in_flight, "kernel_breakdown": breakdown, "library": dm.lib.version,
-        }), flush=True)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and parity["mismatches"]:
@@ -1020,6 +1042,8 @@ def main():
                          "(strong); auto = shards from 4M cells up (below that a sweep is shorter than the halo flag round trip)")
     ap.add_argument("--shard-min-cells", type=int, default=-1, dest="shard_min_cells",
                     help="engine threshold below which sweep loops stay unsharded (-1: engine default, 0: always shard)")
+    ap.add_argument("--extras-timeout", type=float, default=240.0, dest="extras_timeout",
+                    help="seconds the supplementary legs (planets in flight, sharded probe) may take before the main line is printed without them")
     ap.add_argument("--shard-probe-cells", type=int, default=10_000_000, dest="shard_probe_cells",
                     help="N>1, replicas mode: size of the supplementary sharded climate measurement (0: skip)")
     ap.add_argument("--in-flight", type=int, default=4, dest="in_flight",

@@ -465,7 +465,7 @@ struct Mesh {
                         PB_CUDA_CHECK(cudaGetDevice(&dev));
                         PB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
                         PB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_subtree_counts, 256, 0));
-                        subtreeGrid = (coop && perSm > 0) ? x.sm_count * std::min(perSm, 4) : 0;     // latency-bound rounds: more resident threads, fewer items per thread
+                        subtreeGrid = (coop && perSm > 0) ? x.sm_count : 0;     // one CTA per SM: several planets in flight must be able to hold their cooperative grids side by side
                     }
                     if (subtreeGrid > 0) {
                         const int* po = order.p; const int* pp = pos.p; const int* pt = drainTarget.p; const uint8_t* pi = isOcean;
