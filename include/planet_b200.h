@@ -60,6 +60,10 @@ pb_status pb_synchronize(pb_context* ctx);
  * the other host-serial stages (assignDistanceField); "device": the one-CTA CUDA kernel k_flood_heap (≈ 8x slower:
  * a single warp retires the dependent chain at ~0.1 instructions per cycle).  Everything else of the function stays
  * on the GPU either way and the results are identical.
+ * "flow": how the hydraulic flow accumulation (js/terrain-post.js:604-611) runs — "doubling": subtree sizes by pointer
+ * doubling (the additions are integer-valued below 2^24 land cells, hence exact in any order), "ordered": the sync-free
+ * dataflow in the reference's order (always used from 2^24 land cells up), "auto" (default): doubling, except while
+ * several contexts are alive in the process (planets in flight on one GPU), where the ordered form is used.
  * "mesh_order": "canonical" (default) — pb_triangulate_sphere / pb_mesh_create_from_points / the coarse mesh of
  * pb_generate_coarse_plates use the device mesh builder, whose neighbour rows start at a canonical triangle; "delaunator" —
  * they use the reference's own row starts (delaunator@5.0.1's triangle numbering, serial host algorithm, see

@@ -16,9 +16,13 @@ namespace pb {
 
 inline double js_round(double x) { return floor(x + 0.5); }   // Math.round
 
+// contexts alive in this process: several planets in flight on one GPU (one context + stream + host thread each) share the SMs
+inline std::atomic<int>& live_contexts() { static std::atomic<int> n{0}; return n; }
+
 struct Context {
     int device = 0;
     int pointerMode = PB_POINTER_HOST;
+    int flowMode = 0;                   // option "flow": 0 auto, 1 doubling (integer-exact subtree sizes), 2 ordered (dataflow)
     bool meshOrderDelaunator = false;   // option "mesh_order": "canonical" (device builder) | "delaunator" (reference's own row starts, host)
     bool floodOnHost = true;       // option "flood": "host" (default) = the serial heap pass of priorityFloodCarve on a host core, "device" = k_flood_heap
     Exec ex;
@@ -33,7 +37,11 @@ struct Context {
 #endif
         ex.ticket = ticket.ensure(4);
         ex.prof = &profiler;
+        live_contexts()++;
     }
+    ~Context() { live_contexts()--; }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
     void bind() const {
 #if PB_CUDA
         PB_CUDA_CHECK(cudaSetDevice(device));
@@ -456,7 +464,11 @@ struct Mesh {
             if (hydraulicThisIter) {
                 if (glacialThisIter) sort_land_desc(elev, landCount);
                 x.for_each(N, ReceiversK{g, elev, isOcean, ndist.p, drainTarget.p, cellDist.p});
-                if (landCount < (1 << 24) && !getenv("PB_ORDERED_FLOW")) {
+                // Planets in flight on other streams: the cooperative doubling kernel of one planet next to the backing-off
+                // dataflow kernels of another was observed to hang (grids that need all their CTAs resident next to grids whose
+                // lanes sleep); with more than one context alive the accumulation therefore takes the ordered dataflow form.
+                const bool doubling = ctx->flowMode == 1 || (ctx->flowMode == 0 && live_contexts() <= 1 && !getenv("PB_ORDERED_FLOW"));
+                if (landCount < (1 << 24) && doubling) {
                     // integer-valued, exact in f32: subtree sizes by pointer doubling (pb_erode.h)
                     int* jA = k0.p; int* jB = k1.p; int* cA = k2.p; int* cB = cnt.p;       // free until SolvePrepK
 #if PB_CUDA

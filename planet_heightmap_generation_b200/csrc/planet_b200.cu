@@ -106,6 +106,9 @@ pb_status pb_set_option(pb_context* ctx, const char* name, const char* value) {
         if (n == "flood") {
             need(v == "device" || v == "host", "flood must be 'device' or 'host'");
             ctx->c.floodOnHost = v == "host";
+        } else if (n == "flow") {
+            need(v == "auto" || v == "doubling" || v == "ordered", "flow must be 'auto', 'doubling' or 'ordered'");
+            ctx->c.flowMode = v == "doubling" ? 1 : v == "ordered" ? 2 : 0;
         } else if (n == "mesh_order") {
             need(v == "canonical" || v == "delaunator", "mesh_order must be 'canonical' or 'delaunator'");
             ctx->c.meshOrderDelaunator = v == "delaunator";

@@ -204,3 +204,22 @@ def test_argument_errors(backend, planet_small):
     m = M(); m.numRegions = mesh.numRegions; m.adjOffset = mesh.adjOffset; m.adjList = bad
     with pytest.raises(PlanetB200Error):
         DeviceMesh(m, xyz, lib=backend)
+
+
+@pytest.mark.parametrize("flow", ["doubling", "ordered"])
+def test_flow_accumulation_forms_match(backend, oracle, planet_medium, flow):
+    """Hydraulic flow accumulation (js/terrain-post.js:604-611): subtree sizes by pointer doubling and the ordered dataflow give
+    the oracle's drainage targets, flow and elevations bit for bit."""
+    from planet_heightmap_generation_b200.terrain_post import erodeComposite
+    mesh, xyz, nd, elev = planet_medium()
+    ocean = (elev <= 0).astype(np.uint8)
+    want = elev.copy()
+    o_t, o_f, o_l = oracle.erode_composite(mesh, want, xyz, ocean, 6, 0.0003, 0.5, 1.0, 1, 1.16, 0.015, 2, 0.5, nd, capture_iter=4)
+    dm = _dm(backend, mesh, xyz)
+    dm.set_option("flow", flow)
+    got = elev.copy()
+    taps = erodeComposite(dm, got, xyz, ocean, 6, 0.0003, 0.5, 1.0, 1, 1.16, 0.015, 2, 0.5, nd, capture_iter=4)
+    land = ocean == 0
+    assert_bit_equal(taps[0], o_t, "drainTarget")
+    assert_bit_equal(taps[1][land], o_f[land], "flow")
+    assert_bit_equal(got, want, "erodeComposite")
