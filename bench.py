@@ -674,6 +674,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler starts before the last warm-up steps: the first nvidia-smi queries of a fresh process take tens of
+    # milliseconds of driver time each and must not fall into the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup - 1, 0)):
         step_device()
     # last warm-up step is fully profiled: it names the dominant kernel (largest total device time)
@@ -691,20 +696,22 @@ def run_b200(args):
         for p in rows[:30]:
             log(f"   {p['ms']:10.3f} ms  {p['launches']:6d}x  {p['name']}")
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = dm.launch_count()
     # events around the launches of the dominant kernel and of the most-launched sweep kernel only
     dm.profile_start(dominant if dominant == sweep_kernel else "|".join([dominant, sweep_kernel]))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    marks = []
     for _ in range(args.steps):
         step_device()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append(e)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    ms_steps = [round(a.elapsed_time(b), 1) for a, b in zip([ev0] + marks[:-1], marks)]
     prof = dm.profile_stop()
     launches = dm.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -878,7 +885,7 @@ def run_b200(args):
     # ---- the main line is complete here; the supplementary legs below run under a watchdog ----------------------------
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if shards_mode else "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "ms_steps": ms_steps, "higher_is_better": True, "scaling": "strong" if shards_mode else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "impl": "b200", "config": bench_config(args, world), "land_cells": land, "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
