@@ -1033,9 +1033,18 @@ struct LandWeightsK {
         for (int k = 0; k < PB_ROW_FAST; k++) out[(size_t)PB_ROW_FAST * i + k] = k < deg ? wt[b + k] : 0.0f;
     }
 };
+struct LandIndexK { const int* landRow; int* landIndex; PB_DEV void operator()(int i) const { landIndex[landRow[i]] = i; } };
+struct LandRangeK {      // out[0], out[1] = first land item with row >= lo, >= hi (the item range of a rank's cell-id range)
+    const int* landRow; int n; int lo, hi; int* out;
+    PB_DEV int lower(int key) const { int a = 0, b = n; while (a < b) { const int m = (a + b) >> 1; if (landRow[m] < key) a = m + 1; else b = m; } return a; }
+    PB_DEV void operator()(int) const { out[0] = lower(lo); out[1] = lower(hi); }
+};
 struct ShadowLandK {
+    static constexpr bool kItems = true;
     Csr g; const int* landRow; const PackedRow* landPack; const float* landWt; const float* wtCsr; const uint8_t* isLand;
-    const float* src; float* dst; double keepFactor; int sign;
+    const float* src; float* dst; double keepFactor; int sign; const int* landIndex;
+    PB_DEV int row_of(int i) const { return landRow[i]; }
+    PB_DEV void by_row(int r) const { const int i = landIndex[r]; if (i >= 0) (*this)(i); }
     PB_DEV void operator()(int i) const {
         const int r = landRow[i];
         RowIds row; int deg;

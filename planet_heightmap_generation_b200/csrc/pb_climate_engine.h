@@ -28,7 +28,7 @@ struct Climate {
     DevBuf<uint8_t> plateTable, contPlate, flagA, flagB, flagC, noiseTab;
     DevBuf<double> samples, scalars;
     DevBuf<SplineDev> splines;
-    DevBuf<int> landRow; DevBuf<PackedRow> landPack; DevBuf<float> landWt; int nLand = 0;
+    DevBuf<int> landRow, landIndex; DevBuf<PackedRow> landPack; DevBuf<float> landWt; int nLand = 0, landLo = 0, landHi = 0;
 
     explicit Climate(Mesh* mesh) : m(mesh), N(mesh->N) {}
 
@@ -290,7 +290,16 @@ struct Climate {
             cnt.ensure(160);
             m->prims.compact_flagged(x, isLand, N, landRow.ensure(N), cnt.p + 152);
             nLand = m->read_int(cnt.p + 152);
-            if (nLand > 0) x.for_each(nLand, LandPackK{landRow.p, g.pack, landPack.ensure(nLand)});
+            if (nLand > 0) {
+                x.for_each(nLand, LandPackK{landRow.p, g.pack, landPack.ensure(nLand)});
+                x.for_each(N, FillIntK{landIndex.ensure(N), -1});
+                x.for_each(nLand, LandIndexK{landRow.p, landIndex.p});
+                landLo = 0; landHi = nLand;
+                if (sweeps_sharded(*m)) {       // the items of this rank's cell-id range
+                    x.for_each(1, LandRangeK{landRow.p, nLand, m->shards->lo, m->shards->hi, cnt.p + 153});
+                    landLo = m->read_int(cnt.p + 153); landHi = m->read_int(cnt.p + 154);
+                }
+            }
         }
         for (int s = 0; s < 2; s++) {
             const std::string name = s == 0 ? "summer" : "winter";
@@ -305,11 +314,11 @@ struct Climate {
             {
                 const float* xyzp = m->xyz.p;
                 auto make = [=](const float* in, float* out) { return AdvectK{g, xyzp, isLand, windE, windN, wX, wY, wZ, heightKm, in, out, depletionBase, maxHops}; };
-                if (landOk && nLand > 0 && !sweeps_sharded(*m)) {
+                if (landOk && nLand > 0) {
                     // ocean cells keep their initial moisture (:122): only the land rows are swept, 32 working lanes per warp
                     dev_copy(bufB, src, sizeof(float) * (size_t)N, 2, x.stream);
                     const int* lr = landRow.p;
-                    sweep_loop_items(*m, nLand, src, maxHops, bufB, [=](const float* in, float* out) { return OverRowsK<AdvectK>{lr, make(in, out)}; });
+                    sweep_loop_items(*m, nLand, landLo, landHi, src, maxHops, bufB, [=](const float* in, float* out) { return OverRowsK<AdvectK>{lr, make(in, out)}; });
                 } else
                     sweep_loop(*m, src, maxHops, bufB, make);
             }
@@ -324,7 +333,7 @@ struct Climate {
             float* ping = conv; float* pong = m->tmp.ensure(N);            // nor is the convergence field
             dev_copy(shadowField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
             dev_copy(windwardField, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);
-            const bool compact = landOk && !sweeps_sharded(*m);      // land-compacted records (pb_climate.h: ShadowLandK)
+            const bool compact = landOk && nLand > 0;      // land-compacted records (pb_climate.h: ShadowLandK)
             for (int dir = 0; dir < 2; dir++) {
                 const float* wt = dir == 0 ? upWt.p : dnWt.p;
                 const double keep = dir == 0 ? 1 - shadowDecay : 1 - windwardDecay;
@@ -334,8 +343,8 @@ struct Climate {
                     dev_copy(pong, rainShadow, sizeof(float) * (size_t)N, 2, x.stream);     // ocean rows are never written: both buffers hold them
                     float* lw = landWt.ensure((size_t)PB_ROW_FAST * nLand);
                     x.for_each(nLand, LandWeightsK{g, landRow.p, wt, lw});
-                    const int* lr = landRow.p; const PackedRow* lp = landPack.p;
-                    sweep_loop_items(*m, nLand, ping, hops, pong, [=](const float* in, float* out) { return ShadowLandK{g, lr, lp, lw, wt, isLand, in, out, keep, sign}; });
+                    const int* lr = landRow.p; const PackedRow* lp = landPack.p; const int* li = landIndex.p;
+                    sweep_loop_items(*m, nLand, landLo, landHi, ping, hops, pong, [=](const float* in, float* out) { return ShadowLandK{g, lr, lp, lw, wt, isLand, in, out, keep, sign, li}; });
                 } else
                     sweep_loop(*m, ping, hops, pong, [=](const float* in, float* out) { return ShadowSweepK{g, isLand, wt, in, out, keep, sign}; });
                 x.for_each(N, KeepExtremeK{ping, dir == 0 ? shadowField : windwardField, sign});

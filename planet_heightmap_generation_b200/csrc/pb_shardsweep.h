@@ -32,7 +32,12 @@ struct ShardSweepArgs {
     const unsigned* boundaryMask;                   // bit (row - lo) set: the row is on a send list
     int adjRank[kShardMaxAdj]; const int* sendIdx[kShardMaxAdj]; int sendCount[kShardMaxAdj];
     float* peerOut[kShardMaxAdj]; volatile int* peerFlag[kShardMaxAdj];
+    int itemLo, itemHi;                             // item functors: the items whose rows lie in [lo, hi)
 };
+
+template <class F, class = void> struct ShardIsItems { static constexpr bool value = false; };
+template <class F> struct ShardIsItems<F, decltype((void)F::kItems)> { static constexpr bool value = true; };
+template <class F> PB_DEV void shard_do_row(const F& f, int row) { if constexpr (ShardIsItems<F>::value) f.by_row(row); else f(row); }
 
 #if PB_CUDA
 template <class F>
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(256) k_shard_sweep(F f, const float* out, cons
             int p = 0, base = 0;
             while (j >= base + a.sendCount[p]) base += a.sendCount[p++];
             const int row = a.sendIdx[p][j - base];
-            f(row);                                    // a row on two lists is computed twice: same value
+            shard_do_row(f, row);                      // a row on two lists is computed twice: same value
             a.peerOut[p][row] = out[row];
             pushed = true;
         }
@@ -69,10 +74,18 @@ __global__ void __launch_bounds__(256) k_shard_sweep(F f, const float* out, cons
         return;
     }
     const int nCtas = gridDim.x - a.nBoundaryCtas;
-    for (int i = a.lo + (blockIdx.x - a.nBoundaryCtas) * blockDim.x + threadIdx.x; i < a.hi; i += nCtas * blockDim.x) {
-        const int k = i - a.lo;
-        const bool boundary = a.boundaryMask && ((a.boundaryMask[k >> 5] >> (k & 31)) & 1u);
-        if (!boundary) f(i);
+    if constexpr (ShardIsItems<F>::value) {
+        for (int i = a.itemLo + (blockIdx.x - a.nBoundaryCtas) * blockDim.x + threadIdx.x; i < a.itemHi; i += nCtas * blockDim.x) {
+            const int k = f.row_of(i) - a.lo;
+            const bool boundary = a.boundaryMask && ((a.boundaryMask[k >> 5] >> (k & 31)) & 1u);
+            if (!boundary) f(i);
+        }
+    } else {
+        for (int i = a.lo + (blockIdx.x - a.nBoundaryCtas) * blockDim.x + threadIdx.x; i < a.hi; i += nCtas * blockDim.x) {
+            const int k = i - a.lo;
+            const bool boundary = a.boundaryMask && ((a.boundaryMask[k >> 5] >> (k & 31)) & 1u);
+            if (!boundary) f(i);
+        }
     }
 }
 // my range of `src` → the same range of every peer's buffer
@@ -228,12 +241,15 @@ struct SweepShards {
     }
 
     // `passes` sweeps dst = F(src) over the sharded rows; field is the replicated array (whole on entry and on exit)
+    // itemLo/itemHi >= 0: `make` builds an item functor (kItems) over a compacted list; only those items are swept, every other
+    // cell keeps the value it has in `field` (both buffers start as the field)
     template <class Make>
-    void run(float* field, int passes, const Make& make) {
+    void run(float* field, int passes, const Make& make, int itemLo = -1, int itemHi = -1) {
         const Exec& x = m->ex();
         const cudaStream_t s = x.stream;
         const int nA = (int)adj.size();
         dev_copy(buf[0], field, sizeof(float) * (size_t)N, 2, s);
+        if (itemLo >= 0) dev_copy(buf[1], field, sizeof(float) * (size_t)N, 2, s);
         barrier();                                  // every rank has left the previous loop: its buffers may be written
         ShardSweepArgs a{};
         a.lo = lo; a.hi = hi; a.flags = ctl; a.ticket = ticket.p; a.nAdj = nA; a.sendTotal = sendTotal;
@@ -243,6 +259,7 @@ struct SweepShards {
             a.peerFlag[p] = peers[adj[p]].ctl + rank;
         }
         a.nBoundaryCtas = nA ? std::max(1, std::min((sendTotal + 255) / 256, 32)) : 0;
+        a.itemLo = itemLo; a.itemHi = itemHi;
         const int rows = hi - lo;
         const int grid = a.nBoundaryCtas + std::max(1, std::min((rows + 255) / 256, x.sm_count * 8 - a.nBoundaryCtas));
         for (int k = 1; k <= passes; k++) {
@@ -261,10 +278,14 @@ struct SweepShards {
                 for (int p = 0; p < nA; p++) while (((volatile int*)a.flags)[a.adjRank[p]] < a.waitValue) std::this_thread::yield();
             std::atomic_thread_fence(std::memory_order_seq_cst);
             for (int p = 0; p < nA; p++)
-                for (int j = 0; j < a.sendCount[p]; j++) { const int row = a.sendIdx[p][j]; f(row); a.peerOut[p][row] = out[row]; }
+                for (int j = 0; j < a.sendCount[p]; j++) { const int row = a.sendIdx[p][j]; shard_do_row(f, row); a.peerOut[p][row] = out[row]; }
             std::atomic_thread_fence(std::memory_order_seq_cst);
             for (int p = 0; p < nA; p++) *a.peerFlag[p] = a.setValue;
-            for (int i = lo; i < hi; i++) { const int q = i - lo; if (!((a.boundaryMask[q >> 5] >> (q & 31)) & 1u)) f(i); }
+            if constexpr (ShardIsItems<decltype(f)>::value) {
+                for (int i = itemLo; i < itemHi; i++) { const int q = f.row_of(i) - lo; if (!((a.boundaryMask[q >> 5] >> (q & 31)) & 1u)) f(i); }
+            } else {
+                for (int i = lo; i < hi; i++) { const int q = i - lo; if (!((a.boundaryMask[q >> 5] >> (q & 31)) & 1u)) f(i); }
+            }
 #endif
         }
 #if PB_CUDA
@@ -302,11 +323,12 @@ void sweep_loop(Mesh& m, float* field, int passes, float* scratch, const Make& m
     if (src != field) dev_copy(field, src, sizeof(float) * (size_t)m.N, 2, m.ex().stream);
 }
 inline bool sweeps_sharded(const Mesh& m) { return m.shards && m.shards->active(); }
-// unsharded loop over a compacted item list (`count` items per sweep); scratch must already hold the values of the cells the
-// items never write
+// loop over a compacted item list (`count` items, rows ascending; in a sharded run this rank sweeps the items [itemLo, itemHi) of
+// its cell-id range); scratch must already hold the values of the cells the items never write
 template <class Make>
-void sweep_loop_items(Mesh& m, int count, float* field, int passes, float* scratch, const Make& make) {
+void sweep_loop_items(Mesh& m, int count, int itemLo, int itemHi, float* field, int passes, float* scratch, const Make& make) {
     if (passes <= 0) return;
+    if (m.shards && m.shards->active()) { m.shards->run(field, passes, make, itemLo, itemHi); return; }
     float* src = field; float* dst = scratch;
     for (int p = 0; p < passes; p++) {
         m.ex().for_each(count, make((const float*)src, dst));

@@ -123,8 +123,16 @@ struct SmoothFieldK {
 };
 
 // any row functor over a compacted row list: the lanes of a warp all carry work (rows outside the list are not visited)
+// Item functors (kItems): operator()(i) handles item i of a compacted list, row_of(i) is its row, by_row(r) handles row r when
+// the caller only knows the row (the boundary rows of a sharded sweep).
 template <class F>
-struct OverRowsK { const int* rows; F f; PB_DEV void operator()(int i) const { f(rows[i]); } };
+struct OverRowsK {
+    static constexpr bool kItems = true;
+    const int* rows; F f;
+    PB_DEV void operator()(int i) const { f(rows[i]); }
+    PB_DEV int row_of(int i) const { return rows[i]; }
+    PB_DEV void by_row(int r) const { f(r); }
+};
 
 // js/planet-worker.js:51-54
 struct IsOceanK {
