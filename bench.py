@@ -380,6 +380,8 @@ def algorithmic_bytes(name: str, N: int, E: int, land: int):
         "pb::DiffuseWarmthK": csr + 12 * N,
         # offsets + isLand + src + dst for every cell; adj + weight for land rows
         "pb::ShadowSweepK": 4 * (N + 1) + 9 * N + int(8 * E * lf),
+        # the same sweep over compacted land rows: counted with the row-indexed form's bytes so that the two are comparable
+        "pb::ShadowLandK": 4 * (N + 1) + 9 * N + int(8 * E * lf),
         # CSR + xyz 12 + wind3d 12 + windE/N 8 + height 4 + src 4 + dst 4 + mask 1
         "pb::AdvectK": csr + 45 * N,
         "cub::DeviceRadixSort::SortPairs": 4 * 16 * land,
@@ -825,9 +827,9 @@ def run_b200(args):
 
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (1M cells); only
     # quoted when the bench runs the size the capture was taken at
-    ncu_traffic = {"pb::k_flood_heap": (40.1e6, "profiles/r01_flood_heap_ncu.md (240 310 land cells)"),
+    ncu_traffic = {"pb::k_carve_lift": (42.2e6, "profiles/r02_kernels_ncu.md (same seeded planet: 41.25 MB read + 0.97 MB written)"),
+                   "pb::SolveK": (35.7e6, "profiles/r02_kernels_ncu.md (34.08 MB read + 1.65 MB written)"),
                    "pb::SmoothFieldK": (32.0e6, "profiles/r01_sweeps_ncu.md"),
-                   "pb::ShadowSweepK": (62.0e6, "profiles/r01_sweeps_ncu.md (37.3 MB read + 19-30 MB written)"),
                    "pb::StarK": (133.2e6, "profiles/r01_mesh_plates_ncu.md")}
 
     def roof(kernel):
