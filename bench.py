@@ -150,16 +150,47 @@ CLIMATE_REPLY_F32 = (  # the per-cell arrays of the worker's climateDone reply (
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  Default: NVML from a background thread of this process (a few
+    cheap queries every 250 ms); BENCH_SAMPLER=smi uses an `nvidia-smi -lms` child process instead (the form the profiling recipe
+    shows — on some boxes its queries were seen to stall the launching process for hundreds of milliseconds), BENCH_SAMPLER=none
+    switches sampling off."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
+        self.mode = os.environ.get("BENCH_SAMPLER", "nvml")
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+
+    def _nvml_loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((sm, mx, [k for k, b in bits.items() if r & b]))
+                time.sleep(0.25)
+        except Exception as e:      # sampling is evidence, not the measurement
+            self.samples.append(("error", str(e)))
 
     def start(self):
+        if self.mode == "none":
+            return
+        if self.mode == "nvml":
+            import threading
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
@@ -170,7 +201,17 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "sampler": self.mode}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            good = [x for x in self.samples if x and x[0] != "error"]
+            if good:
+                reasons = sorted({r for x in good for r in x[2]})
+                out.update(sm_mhz=float(np.median([x[0] for x in good])), sm_max_mhz=good[0][1], reasons=reasons, samples=len(good))
+            else:
+                out["error"] = [x[1] for x in self.samples if x and x[0] == "error"][:1]
+            return out
         if not self.proc:
             return out
         time.sleep(0.25)

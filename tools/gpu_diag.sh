@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 240 python bench.py --extras-timeout 100 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.log; echo "bench rc=$?" >> gpurun_out/bench_default.log
+for m in none smi nvml; do
+BENCH_SAMPLER=$m timeout 70 python bench.py --steps 6 --warmup 2 --no-cpu --in-flight 0 > gpurun_out/sampler_$m.json 2> gpurun_out/sampler_$m.log; echo "rc=$?" >> gpurun_out/sampler_$m.log
 python -c "
 import json
-d=json.loads(open('gpurun_out/bench_default.json').read()); print(d['ms_per_step'], d['ms_steps'], d['e2e']['ms_per_step'], d['clocks'])"
+d=json.loads(open('gpurun_out/sampler_$m.json').read()); print('$m', d['ms_per_step'], d['ms_steps'], d['clocks'])"
+done
