@@ -711,9 +711,9 @@ def run_b200(args):
         if do_clim:
             cl.computeClimate(dm, state["elev"], state["pio"], r_plate, SEED, 0.0, 0.0, 0.3, out_koppen=koppen)
         if step_sync:
-            torch.cuda.synchronize()      # a step ends when its last kernel has run (the next planet's host stages do not run ahead)
+            torch.cuda.synchronize()      # diagnostic (BENCH_STEP_SYNC=1): no run-ahead of the next step's host stages
 
-    step_sync = os.environ.get("BENCH_STEP_SYNC", "1") != "0"
+    step_sync = os.environ.get("BENCH_STEP_SYNC", "0") != "0"
 
     def barrier():
         torch.cuda.synchronize()
