@@ -20,6 +20,10 @@
 #include <atomic>
 #include <typeinfo>
 #include <map>
+#include <mutex>
+#include <thread>
+#include <tuple>
+#include <functional>
 #include <cxxabi.h>
 
 #if defined(__CUDACC__) && !defined(PB_EMUL)
@@ -55,20 +59,72 @@ struct Error : std::runtime_error {
 // ---------------------------------------------------------------------------------------------
 // memory
 // ---------------------------------------------------------------------------------------------
+// Device allocations go through a small per-process cache: freed blocks are kept (by device and size) and handed out again.
+// Every generate call builds and drops a coarse mesh, staging arrays and scratch buffers of the same sizes; without the cache
+// that is ≈ 60 cudaMalloc / cudaFree calls per planet, each a device-wide synchronisation inside the driver.  Blocks above
+// the cache budget (PB_ALLOC_CACHE_MB, default 8 GiB per process) are returned to the driver.  A block is only handed back to
+// the host thread that freed it: each planet in flight has its own thread and stream, and a block dropped while that stream
+// still has kernels in flight must not be written from another stream (cudaFree used to provide that by synchronising).
+struct AllocCache {
+    std::mutex mu;
+    typedef std::tuple<int, size_t, size_t> Key;                  // (device, bytes, freeing thread)
+    std::multimap<Key, void*> freeBlocks;
+    std::map<void*, std::pair<int, size_t>> live;
+    static size_t me() { return std::hash<std::thread::id>()(std::this_thread::get_id()); }
+    size_t cached = 0, budget;
+    AllocCache() { const char* e = getenv("PB_ALLOC_CACHE_MB"); budget = (size_t)(e ? atoll(e) : 8192) << 20; }
+    static AllocCache& get() { static AllocCache* c = new AllocCache(); return *c; }     // never destroyed: outlives every context
+};
 inline void* dev_alloc(size_t bytes) {
     if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    AllocCache& c = AllocCache::get();
+    int dev = 0;
 #if PB_CUDA
-    void* p = nullptr;
-    PB_CUDA_CHECK(cudaMalloc(&p, bytes));
-    return p;
-#else
-    void* p = malloc(bytes);
-    if (!p) throw Error("malloc failed");
-    return p;
+    PB_CUDA_CHECK(cudaGetDevice(&dev));
 #endif
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.freeBlocks.find(AllocCache::Key{dev, bytes, AllocCache::me()});
+        if (it != c.freeBlocks.end()) {
+            void* p = it->second;
+            c.freeBlocks.erase(it);
+            c.cached -= bytes;
+            c.live[p] = {dev, bytes};
+            return p;
+        }
+    }
+    void* p = nullptr;
+#if PB_CUDA
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {          // out of memory: give the cached blocks back and retry once
+        cudaGetLastError();
+        std::vector<void*> drop;
+        { std::lock_guard<std::mutex> lk(c.mu); for (auto& kv : c.freeBlocks) drop.push_back(kv.second); c.freeBlocks.clear(); c.cached = 0; }
+        cudaDeviceSynchronize();
+        for (void* q : drop) cudaFree(q);
+        PB_CUDA_CHECK(cudaMalloc(&p, bytes));
+    }
+#else
+    p = malloc(bytes);
+    if (!p) throw Error("malloc failed");
+#endif
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.live[p] = {dev, bytes};
+    return p;
 }
 inline void dev_free(void* p) {
     if (!p) return;
+    AllocCache& c = AllocCache::get();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.live.find(p);
+        if (it != c.live.end()) {
+            const std::pair<int, size_t> key = it->second;
+            c.live.erase(it);
+            if (c.cached + key.second <= c.budget) { c.freeBlocks.insert({AllocCache::Key{key.first, key.second, AllocCache::me()}, p}); c.cached += key.second; return; }
+        }
+    }
 #if PB_CUDA
     cudaFree(p);
 #else
