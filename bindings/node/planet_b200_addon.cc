@@ -26,6 +26,16 @@ pb_climate* g_clim = nullptr;
 #define NEED_MESH(env)                                                        \
     do { if (!g_mesh) { napi_throw_error(env, nullptr, "setMesh() has not been called"); return nullptr; } } while (0)
 
+template <class T> struct napi_type_of;
+template <> struct napi_type_of<float> { static const napi_typedarray_type value = napi_float32_array; };
+template <> struct napi_type_of<double> { static const napi_typedarray_type value = napi_float64_array; };
+template <> struct napi_type_of<int32_t> { static const napi_typedarray_type value = napi_int32_array; };
+template <> struct napi_type_of<uint8_t> { static const napi_typedarray_type value = napi_uint8_array; };
+template <> struct napi_type_of<const float> : napi_type_of<float> {};
+template <> struct napi_type_of<const int32_t> : napi_type_of<int32_t> {};
+template <> struct napi_type_of<const uint8_t> : napi_type_of<uint8_t> {};
+template <> struct napi_type_of<const double> : napi_type_of<double> {};
+
 struct Args {
     napi_env env; size_t argc = 16; napi_value v[16];
     Args(napi_env e, napi_callback_info info) : env(e) { napi_get_cb_info(e, info, &argc, v, nullptr, nullptr); }
@@ -36,14 +46,24 @@ struct Args {
     }
     double num(size_t i, double dflt = 0) const { double d = dflt; if (present(i)) napi_get_value_double(env, v[i], &d); return d; }
     int32_t i32(size_t i, int32_t dflt = 0) const { int32_t d = dflt; if (present(i)) napi_get_value_int32(env, v[i], &d); return d; }
-    template <class T> T* typed(size_t i, size_t* len = nullptr) const {
+    // Typed-array argument i as T*: the element type must be T's (a Float64Array where a Float32Array is expected would be read
+    // as garbage), and — for per-cell arrays, cells() — the length must be the mesh's numRegions: the C ABI reads exactly that
+    // many elements.  A mismatch records an error; the caller raises it as a TypeError before touching the library.
+    mutable const char* error = nullptr;
+    template <class T> T* typed(size_t i, size_t* len = nullptr, size_t want = (size_t)-1) const {
         if (!present(i)) return nullptr;
         napi_typedarray_type t; size_t n; void* data; napi_value buf; size_t off;
-        if (napi_get_typedarray_info(env, v[i], &t, &n, &data, &buf, &off) != napi_ok) return nullptr;
+        if (napi_get_typedarray_info(env, v[i], &t, &n, &data, &buf, &off) != napi_ok) { error = "argument is not a typed array"; return nullptr; }
+        if (t != napi_type_of<T>::value) { error = "typed array has the wrong element type"; return nullptr; }
+        if (want != (size_t)-1 && n != want) { error = "typed array has the wrong length"; return nullptr; }
         if (len) *len = n;
         return static_cast<T*>(data);
     }
+    template <class T> T* cells(size_t i) const { return typed<T>(i, nullptr, g_mesh ? (size_t)pb_mesh_num_regions(g_mesh) : 0); }
+    bool failed() const { return error != nullptr; }
+    napi_value raise() const { napi_throw_type_error(env, nullptr, error); return nullptr; }
 };
+#define ARGS_OK(a) do { if ((a).failed()) return (a).raise(); } while (0)
 
 double prop_num(napi_env env, napi_value obj, const char* name, double dflt = 0) {
     bool has = false; napi_has_named_property(env, obj, name, &has);
@@ -67,7 +87,15 @@ napi_value SetMesh(napi_env env, napi_callback_info info) {
     if (!g_ctx) PB_TRY(env, pb_context_create(0, &g_ctx));
     if (g_clim) { pb_climate_destroy(g_clim); g_clim = nullptr; }
     if (g_mesh) { pb_mesh_destroy(g_mesh); g_mesh = nullptr; }
-    PB_TRY(env, pb_mesh_create(g_ctx, a.i32(0), a.typed<int32_t>(1), a.typed<int32_t>(2), a.typed<float>(3), &g_mesh));
+    const int32_t n = a.i32(0);
+    if (n <= 0) { napi_throw_type_error(env, nullptr, "numRegions must be positive"); return nullptr; }
+    size_t nAdj = 0;
+    const int32_t* off = a.typed<int32_t>(1, nullptr, (size_t)n + 1);
+    const int32_t* adj = a.typed<int32_t>(2, &nAdj);
+    const float* xyz = a.typed<float>(3, nullptr, 3 * (size_t)n);
+    ARGS_OK(a);
+    if (!off || !adj || !xyz || (size_t)off[n] != nAdj) { napi_throw_type_error(env, nullptr, "adjList length must equal adjOffset[numRegions]"); return nullptr; }
+    PB_TRY(env, pb_mesh_create(g_ctx, n, off, adj, xyz, &g_mesh));
     PB_TRY(env, pb_climate_create(g_mesh, &g_clim));
     return undefined(env);
 }
@@ -91,32 +119,37 @@ napi_value ComputeNeighborDist(napi_env env, napi_callback_info info) {
 // warpTerrain(mesh, r_elevation, r_xyz, seed, strength, r_hotspot)                  js/terrain-post.js:233
 napi_value WarpTerrain(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_warp_terrain(g_mesh, a.typed<float>(1), a.num(3), a.num(4), a.typed<float>(5)));
+    (void)(a.cells<float>(1), a.cells<float>(5)); ARGS_OK(a);
+    PB_TRY(env, pb_warp_terrain(g_mesh, a.cells<float>(1), a.num(3), a.num(4), a.cells<float>(5)));
     return undefined(env);
 }
 // smoothElevation(mesh, r_elevation, r_isOcean, iterations, strength)               :317
 napi_value SmoothElevation(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_smooth_elevation(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    (void)(a.cells<float>(1), a.cells<uint8_t>(2)); ARGS_OK(a);
+    PB_TRY(env, pb_smooth_elevation(g_mesh, a.cells<float>(1), a.cells<uint8_t>(2), a.i32(3), a.num(4)));
     return undefined(env);
 }
 // erodeComposite(mesh, r_elevation, r_xyz, r_isOcean, hIters, K, m, dt, tIters, talusSlope, kThermal, gIters,
 //                glacialStrength, neighborDist)                                      :369
 napi_value ErodeComposite(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_erode_composite(g_mesh, a.typed<float>(1), a.typed<uint8_t>(3), a.i32(4), a.num(5), a.num(6), a.num(7), a.i32(8),
+    (void)(a.cells<float>(1), a.cells<uint8_t>(3)); ARGS_OK(a);
+    PB_TRY(env, pb_erode_composite(g_mesh, a.cells<float>(1), a.cells<uint8_t>(3), a.i32(4), a.num(5), a.num(6), a.num(7), a.i32(8),
                                    a.num(9), a.num(10), a.i32(11, 0), a.num(12, 0)));
     return undefined(env);
 }
 // sharpenRidges / applySoilCreep(mesh, r_elevation, r_isOcean, iterations, strength) :713 / :758
 napi_value SharpenRidges(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_sharpen_ridges(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    (void)(a.cells<float>(1), a.cells<uint8_t>(2)); ARGS_OK(a);
+    PB_TRY(env, pb_sharpen_ridges(g_mesh, a.cells<float>(1), a.cells<uint8_t>(2), a.i32(3), a.num(4)));
     return undefined(env);
 }
 napi_value ApplySoilCreep(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_apply_soil_creep(g_mesh, a.typed<float>(1), a.typed<uint8_t>(2), a.i32(3), a.num(4)));
+    (void)(a.cells<float>(1), a.cells<uint8_t>(2)); ARGS_OK(a);
+    PB_TRY(env, pb_apply_soil_creep(g_mesh, a.cells<float>(1), a.cells<uint8_t>(2), a.i32(3), a.num(4)));
     return undefined(env);
 }
 // runPostProcessing(mesh, r_xyz, r_elevation, params, neighborDist, seed, r_hotspot) → {dl_erosionDelta, postTiming}
@@ -130,7 +163,8 @@ napi_value RunPostProcessing(napi_env env, napi_callback_info info) {
     p.hItersOverride = (int32_t)prop_num(env, a.v[3], "hItersOverride", -1);
     const size_t n = (size_t)pb_mesh_num_regions(g_mesh);
     void* d; napi_value delta = new_typed(env, napi_float32_array, n, 4, &d);
-    PB_TRY(env, pb_run_post_processing(g_mesh, a.typed<float>(2), &p, a.num(5), a.typed<float>(6), static_cast<float*>(d), nullptr));
+    (void)(a.cells<float>(2), a.cells<float>(6)); ARGS_OK(a);
+    PB_TRY(env, pb_run_post_processing(g_mesh, a.cells<float>(2), &p, a.num(5), a.cells<float>(6), static_cast<float*>(d), nullptr));
     napi_value out; napi_create_object(env, &out);
     napi_set_named_property(env, out, "dl_erosionDelta", delta);
     double ms[5]; static const char* stage[5] = {"Terrain warp", "Smoothing", "Erosion composite", "Ridge sharpening", "Soil creep"};
@@ -146,9 +180,9 @@ napi_value RunPostProcessing(napi_env env, napi_callback_info info) {
 bool plate_table(const Args& a, size_t first, pb_plate_table* t) {
     size_t n = 0;
     t->ids = a.typed<int32_t>(first, &n); t->n = (int32_t)n;
-    t->isOcean = a.typed<uint8_t>(first + 1); t->pole = a.typed<double>(first + 2);
-    t->omega = a.typed<double>(first + 3); t->density = a.typed<double>(first + 4);
-    return t->ids && t->isOcean && t->pole && t->omega && t->density;
+    t->isOcean = a.typed<uint8_t>(first + 1, nullptr, n); t->pole = a.typed<double>(first + 2, nullptr, 3 * n);
+    t->omega = a.typed<double>(first + 3, nullptr, n); t->density = a.typed<double>(first + 4, nullptr, n);
+    return !a.failed() && t->ids && t->isOcean && t->pole && t->omega && t->density;
 }
 // assignElevation(r_plate, plateIds, plateIsOcean, platePole, plateOmega, plateDensity, plateSeeds:Int32Array, noiseSeed,
 //                 noiseMag, seed, spread, [r_superPlate, sIds, sIsOcean, sPole, sOmega, sDensity])
@@ -174,7 +208,8 @@ napi_value AssignElevation(napi_env env, napi_callback_info info) {
                                      "backArc", "foldRidge", "orogenicPower"};
     for (int k = 0; k < 12; k++) { napi_set_named_property(env, dbg, layers[k], new_typed(env, napi_float32_array, n, 4, &d)); r.debug[k] = static_cast<float*>(d); }
     napi_set_named_property(env, out, "debugLayers", dbg);
-    PB_TRY(env, pb_assign_elevation(g_mesh, &P, a.typed<int32_t>(0), seeds, (int32_t)nSeeds, a.num(7), a.num(8), a.num(9), a.num(10),
+    (void)(a.cells<int32_t>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_assign_elevation(g_mesh, &P, a.cells<int32_t>(0), seeds, (int32_t)nSeeds, a.num(7), a.num(8), a.num(9), a.num(10),
                                     dual ? &SP : nullptr, dual ? a.typed<int32_t>(11) : nullptr, &r));
     return out;
 }
@@ -183,28 +218,33 @@ napi_value AssignElevation(napi_env env, napi_callback_info info) {
 napi_value ComputeWind(napi_env env, napi_callback_info info) {          // (r_elevation, plateIsOceanIds:Int32Array, r_plate, noiseSeed, axialTilt)
     NEED_MESH(env); Args a(env, info);
     size_t nIds = 0; const int32_t* ids = a.typed<int32_t>(1, &nIds);
-    PB_TRY(env, pb_compute_wind(g_clim, a.typed<float>(0), ids, (int32_t)nIds, a.typed<int32_t>(2), a.num(3), a.num(4, 23.5)));
+    (void)(a.cells<float>(0), a.cells<int32_t>(2)); ARGS_OK(a);
+    PB_TRY(env, pb_compute_wind(g_clim, a.cells<float>(0), ids, (int32_t)nIds, a.cells<int32_t>(2), a.num(3), a.num(4, 23.5)));
     return undefined(env);
 }
 napi_value ComputeOceanCurrents(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_compute_ocean_currents(g_clim, a.typed<float>(0)));
+    (void)(a.cells<float>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_compute_ocean_currents(g_clim, a.cells<float>(0)));
     return undefined(env);
 }
 napi_value ComputePrecipitation(napi_env env, napi_callback_info info) {  // (r_elevation, precipitationOffset, landCoverage)
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_compute_precipitation(g_clim, a.typed<float>(0), a.num(1, 0), a.num(2, 0.3)));
+    (void)(a.cells<float>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_compute_precipitation(g_clim, a.cells<float>(0), a.num(1, 0), a.num(2, 0.3)));
     return undefined(env);
 }
 napi_value ComputeTemperature(napi_env env, napi_callback_info info) {    // (r_elevation, temperatureOffset)
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_compute_temperature(g_clim, a.typed<float>(0), a.num(1, 0)));
+    (void)(a.cells<float>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_compute_temperature(g_clim, a.cells<float>(0), a.num(1, 0)));
     return undefined(env);
 }
 napi_value ClassifyKoppen(napi_env env, napi_callback_info info) {        // (r_elevation) → Uint8Array
     NEED_MESH(env); Args a(env, info);
     void* d; napi_value out = new_typed(env, napi_uint8_array, (size_t)pb_mesh_num_regions(g_mesh), 1, &d);
-    PB_TRY(env, pb_classify_koppen(g_clim, a.typed<float>(0), static_cast<uint8_t*>(d)));
+    (void)(a.cells<float>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_classify_koppen(g_clim, a.cells<float>(0), static_cast<uint8_t*>(d)));
     return out;
 }
 napi_value GetClimateField(napi_env env, napi_callback_info info) {       // (name) → typed array
@@ -222,7 +262,8 @@ napi_value GetClimateField(napi_env env, napi_callback_info info) {       // (na
 // smoothField(mesh, field, passes)                                                  js/climate-util.js:5
 napi_value SmoothField(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
-    PB_TRY(env, pb_smooth_field(g_mesh, a.typed<float>(1), a.i32(2)));
+    (void)(a.cells<float>(1)); ARGS_OK(a);
+    PB_TRY(env, pb_smooth_field(g_mesh, a.cells<float>(1), a.i32(2)));
     return undefined(env);
 }
 
@@ -279,8 +320,17 @@ napi_value ProjectCoarsePlates(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
     void* d;
     napi_value out = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_regions(g_mesh), 4, &d);
-    PB_TRY(env, pb_project_coarse_plates(g_mesh, a.i32(0), a.typed<int32_t>(1), a.typed<int32_t>(2), a.typed<float>(3), a.typed<int32_t>(4),
-                                         a.num(5), a.present(6) ? a.i32(6) : -1, static_cast<int32_t*>(d)));
+    // the coarse mesh has its own size: offsets numCoarse + 1, xyz 3 numCoarse, r_plate numCoarse, adjList adjOffset[numCoarse]
+    const int32_t nc = a.i32(0);
+    if (nc <= 0) { napi_throw_type_error(env, nullptr, "numCoarse must be positive"); return nullptr; }
+    size_t nAdj = 0;
+    const int32_t* cOff = a.typed<int32_t>(1, nullptr, (size_t)nc + 1);
+    const int32_t* cAdj = a.typed<int32_t>(2, &nAdj);
+    const float* cXyz = a.typed<float>(3, nullptr, 3 * (size_t)nc);
+    const int32_t* cPlate = a.typed<int32_t>(4, nullptr, (size_t)nc);
+    ARGS_OK(a);
+    if (!cOff || !cAdj || !cXyz || !cPlate || (size_t)cOff[nc] != nAdj) { napi_throw_type_error(env, nullptr, "coarse adjList length must equal adjOffset[numCoarse]"); return nullptr; }
+    PB_TRY(env, pb_project_coarse_plates(g_mesh, nc, cOff, cAdj, cXyz, cPlate, a.num(5), a.present(6) ? a.i32(6) : -1, static_cast<int32_t*>(d)));
     return out;
 }
 // smoothAndReconnectPlatesFlat(r_plate, plateSeeds:Int32Array, numPasses)  in place                                 js/plates.js:241
@@ -288,7 +338,8 @@ napi_value SmoothAndReconnectPlates(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
     size_t ns = 0;
     const int32_t* seeds = a.typed<int32_t>(1, &ns);
-    PB_TRY(env, pb_smooth_and_reconnect_plates(g_mesh, a.typed<int32_t>(0), seeds, (int32_t)ns, a.i32(2)));
+    (void)(a.cells<int32_t>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_smooth_and_reconnect_plates(g_mesh, a.cells<int32_t>(0), seeds, (int32_t)ns, a.i32(2)));
     return undefined(env);
 }
 // buildSuperPlatesFlat(r_plate, ids, isOcean, pole, omega, density) → {r_superPlate, numSuperPlates, pole, omega, isOcean, density}   js/super-plates.js:16
@@ -296,14 +347,15 @@ napi_value BuildSuperPlates(napi_env env, napi_callback_info info) {
     NEED_MESH(env); Args a(env, info);
     size_t P = 0;
     const int32_t* ids = a.typed<int32_t>(1, &P);
-    pb_plate_table t{(int32_t)P, ids, a.typed<uint8_t>(2), a.typed<double>(3), a.typed<double>(4), a.typed<double>(5)};
+    pb_plate_table t{(int32_t)P, ids, a.typed<uint8_t>(2, nullptr, P), a.typed<double>(3, nullptr, 3 * P), a.typed<double>(4, nullptr, P), a.typed<double>(5, nullptr, P)};
     const size_t cap = P < 2 ? 2 : P;
     void *rs, *pole, *om, *oc, *de;
     napi_value trs = new_typed(env, napi_int32_array, (size_t)pb_mesh_num_regions(g_mesh), 4, &rs);
     napi_value tpole = new_typed(env, napi_float64_array, 3 * cap, 8, &pole), tom = new_typed(env, napi_float64_array, cap, 8, &om);
     napi_value toc = new_typed(env, napi_uint8_array, cap, 1, &oc), tde = new_typed(env, napi_float64_array, cap, 8, &de);
     pb_super_plate_table sp{(int32_t)cap, 0, static_cast<double*>(pole), static_cast<double*>(om), static_cast<uint8_t*>(oc), static_cast<double*>(de)};
-    PB_TRY(env, pb_build_super_plates(g_mesh, a.typed<int32_t>(0), &t, static_cast<int32_t*>(rs), &sp));
+    (void)(a.cells<int32_t>(0)); ARGS_OK(a);
+    PB_TRY(env, pb_build_super_plates(g_mesh, a.cells<int32_t>(0), &t, static_cast<int32_t*>(rs), &sp));
     napi_value out, nv; napi_create_object(env, &out); napi_create_double(env, sp.numSuperPlates, &nv);
     napi_set_named_property(env, out, "r_superPlate", trs); napi_set_named_property(env, out, "numSuperPlates", nv);
     napi_set_named_property(env, out, "pole", tpole); napi_set_named_property(env, out, "omega", tom);

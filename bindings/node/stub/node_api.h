@@ -40,6 +40,7 @@ napi_status napi_create_object(napi_env, napi_value* result);
 napi_status napi_create_double(napi_env, double value, napi_value* result);
 napi_status napi_get_undefined(napi_env, napi_value* result);
 napi_status napi_throw_error(napi_env, const char* code, const char* msg);
+napi_status napi_throw_type_error(napi_env, const char* code, const char* msg);
 napi_status napi_define_properties(napi_env, napi_value object, size_t property_count, const napi_property_descriptor* properties);
 #define NAPI_MODULE_INIT() extern "C" napi_value napi_register_module_v1(napi_env env, napi_value exports)
 #ifdef __cplusplus

@@ -397,11 +397,6 @@ PB_GLOBAL void __launch_bounds__(128) k_ordered(F f, int n, int* ticket, unsigne
     }
 }
 
-template <class F>
-PB_GLOBAL void k_single(F f) {
-    f();
-}
-
 // grid-stride loop whose bound lives in device memory (frontier sizes); global thread 0 first runs
 // the functor's block0() hook.
 template <class F>
@@ -469,18 +464,15 @@ struct Exec {
 #endif
     }
 
-    // one logical thread (serial kernels: heap flood)
+#if !PB_CUDA
+    // sequential reference forms of the serial passes (heap flood, capped BFS): host emulation only — the CUDA library has no
+    // single-thread kernel
     template <class F>
     void single(const F& f) const {
         launch_stats().launches++;
-        ProfScope ps(prof, typeid(F).name(), stream);
-#if PB_CUDA
-        k_single<F><<<1, 1, 0, stream>>>(f);
-        PB_CUDA_CHECK(cudaGetLastError());
-#else
         f();
-#endif
     }
+#endif
 };
 
 }  // namespace pb
