@@ -37,8 +37,14 @@ template <> struct napi_type_of<const uint8_t> : napi_type_of<uint8_t> {};
 template <> struct napi_type_of<const double> : napi_type_of<double> {};
 
 struct Args {
-    napi_env env; size_t argc = 16; napi_value v[16];
-    Args(napi_env e, napi_callback_info info) : env(e) { napi_get_cb_info(e, info, &argc, v, nullptr, nullptr); }
+    // napi_get_cb_info fills at most `argc` (in) slots and then stores the ACTUAL argument count: clamp it to the capacity,
+    // otherwise present(i) would read past v[] for a call with more arguments (assignElevationFlat takes 17)
+    static const size_t kMaxArgs = 20;
+    napi_env env; size_t argc = kMaxArgs; napi_value v[kMaxArgs];
+    Args(napi_env e, napi_callback_info info) : env(e) {
+        napi_get_cb_info(e, info, &argc, v, nullptr, nullptr);
+        if (argc > kMaxArgs) argc = kMaxArgs;
+    }
     bool present(size_t i) const {
         if (i >= argc) return false;
         napi_valuetype t; napi_typeof(env, v[i], &t);
@@ -267,6 +273,26 @@ napi_value SmoothField(napi_env env, napi_callback_info info) {
     return undefined(env);
 }
 
+// exportMapPixels(type, width, r_elevation, r_koppen | null) → Uint8ClampedArray(width * width/2 * 4): the ImageData of exportMap
+// (js/planet-mesh.js:1752-1950) — `new ImageData(pixels, width)` + putImageData + canvas.toBlob stay on the JS side
+napi_value ExportMapPixels(napi_env env, napi_callback_info info) {
+    NEED_MESH(env); Args a(env, info);
+    char type[32] = {0}; size_t len = 0;
+    if (!a.present(0) || napi_get_value_string_utf8(env, a.v[0], type, sizeof type, &len) != napi_ok) { napi_throw_type_error(env, nullptr, "export type must be a string"); return nullptr; }
+    const std::string t = type;
+    const uint8_t* koppen = a.cells<uint8_t>(3);
+    const float* elev = a.cells<float>(2);
+    ARGS_OK(a);
+    int32_t mode = t == "landmask" ? PB_COLOR_LAND_MASK : t == "landheightmap" ? PB_COLOR_LAND_HEIGHTMAP : t == "heightmap" ? PB_COLOR_HEIGHTMAP
+                 : t == "biome" ? PB_COLOR_BIOME : t == "koppen" ? PB_COLOR_KOPPEN : PB_COLOR_TERRAIN;
+    if ((mode == PB_COLOR_BIOME || mode == PB_COLOR_KOPPEN) && !koppen) mode = PB_COLOR_TERRAIN;     // no climate yet (:1764-1765, 1788-1793)
+    const int32_t width = a.i32(1);
+    if (width < 2 || width > 65536 || width % 2) { napi_throw_type_error(env, nullptr, "width must be even, 2 … 65536"); return nullptr; }
+    void* px; napi_value out = new_typed(env, napi_uint8_clamped_array, (size_t)width * (size_t)(width / 2) * 4, 1, &px);
+    PB_TRY(env, pb_export_map(g_mesh, mode, width, elev, koppen, static_cast<uint8_t*>(px), nullptr));
+    return out;
+}
+
 // buildSphereFlat(N, jitter, seed) → {numRegions, r_xyz, adjOffset, adjList}; the mesh becomes the retained mesh   js/sphere-mesh.js:174
 napi_value BuildSphere(napi_env env, napi_callback_info info) {
     Args a(env, info);
@@ -384,6 +410,7 @@ NAPI_MODULE_INIT() {
         {"classifyKoppenFlat", nullptr, ClassifyKoppen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"getClimateField", nullptr, GetClimateField, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"smoothField", nullptr, SmoothField, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"exportMapPixels", nullptr, ExportMapPixels, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"buildSphereFlat", nullptr, BuildSphere, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"generateCoarsePlatesFlat", nullptr, GenerateCoarsePlates, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"projectCoarsePlatesFlat", nullptr, ProjectCoarsePlates, nullptr, nullptr, nullptr, napi_default, nullptr},

@@ -130,3 +130,7 @@ export function computeTemperature(mesh, r_xyz, r_elevation, windResult, oceanRe
   return lazyResult(S.map(s => `r_temperature_${s}`), { _tempTiming: [] });
 }
 export function classifyKoppen(mesh, r_elevation, tempResult, precipResult) { return native.classifyKoppenFlat(r_elevation); }
+
+// exportMap's pixels (js/planet-mesh.js:1752-1950) for the main thread: `ctx.putImageData(new ImageData(px, width), 0, 0)` and
+// `canvas.toBlob` replace the tiled WebGL render + readback; type is the reference's export type name.
+export function exportMapPixels(type, width, r_elevation, r_koppen = null) { return native.exportMapPixels(type, width, r_elevation, r_koppen); }

@@ -11,7 +11,8 @@ extern "C" {
 typedef struct napi_env__* napi_env;
 typedef struct napi_value__* napi_value;
 typedef struct napi_callback_info__* napi_callback_info;
-typedef enum { napi_ok = 0 } napi_status;
+typedef enum { napi_ok = 0, napi_invalid_arg, napi_object_expected, napi_string_expected, napi_name_expected, napi_function_expected,
+               napi_number_expected, napi_boolean_expected, napi_array_expected, napi_generic_failure, napi_pending_exception } napi_status;
 typedef enum { napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object, napi_function,
                napi_external, napi_bigint } napi_valuetype;
 typedef enum { napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array,

@@ -307,10 +307,26 @@ pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, 
  *   PB_COLOR_BIOME           smoothBiomeColors(mesh, koppen, r_elevation)         js/planet-mesh.js:30-62 (biomeColor, js/color-map.js:73-114)
  *   PB_COLOR_HEIGHTMAP / PB_COLOR_LAND_HEIGHTMAP / PB_COLOR_LAND_MASK             js/planet-mesh.js:64-80
  *   PB_COLOR_BIOME_RAW       biomeColor(koppen[r], r_elevation[r]) without the neighbour blend
- * r_koppen is only read by the two biome modes.  Arrays follow the context's pointer mode. */
+ *   PB_COLOR_KOPPEN          koppenColor(koppen[r]) = KOPPEN_CLASSES[id].color       js/planet-mesh.js:175-178, js/koppen.js:19-51
+ * r_koppen is only read by the biome and koppen modes.  Arrays follow the context's pointer mode. */
 enum { PB_COLOR_TERRAIN = 0, PB_COLOR_BIOME = 1, PB_COLOR_HEIGHTMAP = 2, PB_COLOR_LAND_HEIGHTMAP = 3, PB_COLOR_LAND_MASK = 4,
-       PB_COLOR_BIOME_RAW = 5 };
+       PB_COLOR_BIOME_RAW = 5, PB_COLOR_KOPPEN = 6 };
 pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation, const uint8_t* r_koppen, float* rgb);
+
+/* ---- equirectangular map export ------------------------------------------------------------------------------------
+ * pb_export_map replaces exportMap(type, width) (js/planet-mesh.js:1752-1950) up to the ImageData the reference puts on its
+ * canvas; the PNG container (canvas.toBlob there) is the caller's.  height = width / 2; rgba = width*height*4 bytes, top
+ * row (north) first, alpha 255.  Export type → colorMode: 'colormap' PB_COLOR_TERRAIN, 'biome' (Satellite) PB_COLOR_BIOME,
+ * 'koppen' PB_COLOR_KOPPEN, 'heightmap' / 'landheightmap' / 'landmask' the three grey modes (black background; the others
+ * clear to THREE.Color(0x1a1a2e)).  Per side s of the mesh one map triangle (centroid of the inner triangle, centroid of
+ * the outer triangle, the begin region) in lon/lat space, drawn twice when it straddles the date line (:1773-1846), flat
+ * colour of the begin region; a pixel takes the LAST triangle in draw order whose closed area contains the pixel centre
+ * (WebGL draws in order with depth LEQUAL at equal z); the render target's unorm8 levels go through the sRGB curve
+ * (:1897-1915).  The rule is evaluated on the pixel grid of the whole image, so the reference's ≤ 2048-pixel tiles (a
+ * browser memory workaround) do not appear.  pixelSide (optional, width*height ints): the side whose triangle owns the
+ * pixel, -1 = background.  Arrays follow the context's pointer mode. */
+pb_status pb_export_map(pb_mesh* mesh, int32_t colorMode, int32_t width, const float* r_elevation, const uint8_t* r_koppen,
+                        uint8_t* rgba, int32_t* pixelSide);
 
 /* ---- triangles: what the worker's `done` / `reapplyDone` / `editDone` replies carry for the renderer ----------------
  * pb_mesh_get_triangles: SphereMesh.triangles / .halfedges (js/sphere-mesh.js:94-100) of the mesh, 3*numTriangles ints

@@ -402,7 +402,7 @@ def classify_imported(mesh, elev):
 
 
 # ---- colour ramps (js/color-map.js, js/planet-mesh.js:30-80) --------------------------------------------------------------
-COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5}
+COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5, "koppen": 6}
 
 
 def region_colors(mesh, mode, elev, koppen=None):
@@ -411,3 +411,26 @@ def region_colors(mesh, mode, elev, koppen=None):
     lib().orc_region_colors(*_mesh_args(mesh), C.c_int(COLOR_MODES[mode]), _p(np.ascontiguousarray(elev, np.float32), C.c_float),
                             _p(k, C.c_uint8), _p(out, C.c_float))
     return out
+
+
+# ---- equirectangular map export (js/planet-mesh.js:1752-1950) ---------------------------------------------------------------
+EXPORT_TYPES = {"colormap": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "koppen": 6}
+
+
+def triangle_centers(mesh, xyz):
+    out = np.empty(3 * mesh.numTriangles, np.float32)
+    lib().orc_triangle_centers(C.c_int(mesh.numTriangles), _p(mesh.triangles, C.c_int32), _p(np.ascontiguousarray(xyz, np.float32), C.c_float),
+                               _p(out, C.c_float))
+    return out
+
+
+def export_map(mesh, xyz, export_type, width, elev, koppen=None):
+    """(rgba uint8[height, width, 4], pixelSide int32[height, width]) — exportMap up to the ImageData; `mesh` needs triangles / halfedges."""
+    h = width // 2
+    rgba = np.empty((h, width, 4), np.uint8)
+    side = np.empty((h, width), np.int32)
+    k = np.zeros(mesh.numRegions, np.uint8) if koppen is None else np.ascontiguousarray(koppen, np.uint8)
+    lib().orc_export_map(*_mesh_args(mesh), C.c_int(mesh.numSides), _p(mesh.triangles, C.c_int32), _p(mesh.halfedges, C.c_int32),
+                         _p(np.ascontiguousarray(xyz, np.float32), C.c_float), C.c_int(EXPORT_TYPES[export_type]), C.c_int(width),
+                         _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(k, C.c_uint8), _p(rgba, C.c_uint8), _p(side, C.c_int32))
+    return rgba, side

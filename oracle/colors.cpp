@@ -68,11 +68,19 @@ void biome_color(int koppen, double elevation, double c[3]) {   // js/color-map.
     c[0] = r; c[1] = g; c[2] = b;
 }
 
+const double KOPPEN[31][3] = {                           // KOPPEN_CLASSES[i].color, js/koppen.js:19-51
+    {0.29, 0.44, 0.65}, {0.00, 0.00, 1.00}, {0.00, 0.47, 1.00}, {0.27, 0.67, 0.98}, {1.00, 0.00, 0.00}, {1.00, 0.59, 0.59},
+    {0.96, 0.65, 0.00}, {1.00, 0.86, 0.39}, {0.78, 1.00, 0.31}, {0.39, 1.00, 0.31}, {0.20, 0.78, 0.00}, {1.00, 1.00, 0.00},
+    {0.78, 0.78, 0.00}, {0.59, 0.59, 0.00}, {0.59, 1.00, 0.59}, {0.39, 0.78, 0.39}, {0.20, 0.59, 0.20}, {0.00, 1.00, 1.00},
+    {0.22, 0.78, 1.00}, {0.00, 0.49, 0.49}, {0.00, 0.27, 0.37}, {0.90, 0.50, 1.00}, {0.70, 0.35, 0.85}, {0.50, 0.20, 0.65},
+    {0.35, 0.10, 0.45}, {0.67, 0.69, 1.00}, {0.43, 0.47, 0.78}, {0.29, 0.31, 0.78}, {0.20, 0.00, 0.53}, {0.70, 0.70, 0.70},
+    {0.41, 0.41, 0.41}};
+
 }  // namespace
 
 extern "C" {
 // mode: 0 terrain (elevationToColor), 1 biome smoothed (smoothBiomeColors), 2 heightmap, 3 land heightmap, 4 land mask,
-//       5 biome unsmoothed (biomeColor)
+//       5 biome unsmoothed (biomeColor), 6 koppenColor (js/planet-mesh.js:175-178: `KOPPEN_CLASSES[classId] || KOPPEN_CLASSES[0]`)
 void orc_region_colors(int N, const int32_t* off, const int32_t* adj, int mode, const float* elev, const uint8_t* koppen, float* rgb) {
     std::vector<float> raw;
     if (mode == 1) raw.resize(3 * (size_t)N);
@@ -84,6 +92,7 @@ void orc_region_colors(int N, const int32_t* off, const int32_t* adj, int mode, 
         else if (mode == 2) { const double t = js::max(0, js::min(1, (height_km(e) + 5) / 11)); c[0] = c[1] = c[2] = t; }
         else if (mode == 3) { if (e > 0) { const double t = js::max(0, js::min(1, height_km(e) / 6)); c[0] = c[1] = c[2] = t; } }
         else if (mode == 4) { if (e > 0) c[0] = c[1] = c[2] = 1; }
+        else if (mode == 6) { const int id = koppen[r] <= 30 ? koppen[r] : 0; for (int k = 0; k < 3; k++) c[k] = KOPPEN[id][k]; }
         float* dst = mode == 1 ? raw.data() : rgb;
         for (int k = 0; k < 3; k++) dst[3 * r + k] = js::f32(c[k]);
     }

@@ -74,6 +74,7 @@ SYMBOLS = {
     "pb_derive_synthetic_plates": (C.c_int, [_vp, _vp, _vp]),
     "pb_classify_imported_regions": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pb_region_colors": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "pb_export_map": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pb_mesh_num_triangles": (_i32, [_vp]),
     "pb_mesh_get_triangles": (C.c_int, [_vp, _vp, _vp]),
     "pb_mesh_get_adj_triangles": (C.c_int, [_vp, _vp]),

@@ -64,7 +64,21 @@ PB_DEV Rgb biome_color(int id, double elevation) {       // biomeColor
     return c;
 }
 
-enum ColorMode { COLOR_TERRAIN = 0, COLOR_BIOME = 1, COLOR_HEIGHTMAP = 2, COLOR_LAND_HEIGHTMAP = 3, COLOR_LAND_MASK = 4, COLOR_BIOME_RAW = 5 };
+// koppenColor: KOPPEN_CLASSES[classId].color, ids outside the table take class 0 (js/planet-mesh.js:175-178, js/koppen.js:19-51)
+PB_DEV Rgb koppen_class_color(int id) {
+    const double T[31][3] = {
+        {0.29, 0.44, 0.65}, {0.00, 0.00, 1.00}, {0.00, 0.47, 1.00}, {0.27, 0.67, 0.98}, {1.00, 0.00, 0.00}, {1.00, 0.59, 0.59},
+        {0.96, 0.65, 0.00}, {1.00, 0.86, 0.39}, {0.78, 1.00, 0.31}, {0.39, 1.00, 0.31}, {0.20, 0.78, 0.00}, {1.00, 1.00, 0.00},
+        {0.78, 0.78, 0.00}, {0.59, 0.59, 0.00}, {0.59, 1.00, 0.59}, {0.39, 0.78, 0.39}, {0.20, 0.59, 0.20}, {0.00, 1.00, 1.00},
+        {0.22, 0.78, 1.00}, {0.00, 0.49, 0.49}, {0.00, 0.27, 0.37}, {0.90, 0.50, 1.00}, {0.70, 0.35, 0.85}, {0.50, 0.20, 0.65},
+        {0.35, 0.10, 0.45}, {0.67, 0.69, 1.00}, {0.43, 0.47, 0.78}, {0.29, 0.31, 0.78}, {0.20, 0.00, 0.53}, {0.70, 0.70, 0.70},
+        {0.41, 0.41, 0.41}};
+    if (id < 0 || id > 30) id = 0;
+    return {T[id][0], T[id][1], T[id][2]};
+}
+
+enum ColorMode { COLOR_TERRAIN = 0, COLOR_BIOME = 1, COLOR_HEIGHTMAP = 2, COLOR_LAND_HEIGHTMAP = 3, COLOR_LAND_MASK = 4, COLOR_BIOME_RAW = 5,
+                 COLOR_KOPPEN = 6 };
 
 struct RegionColorK {
     int mode; const float* elev; const uint8_t* koppen; float* rgb;
@@ -73,6 +87,7 @@ struct RegionColorK {
         Rgb c{0, 0, 0};
         if (mode == COLOR_TERRAIN) c = terrain_color(e);
         else if (mode == COLOR_BIOME || mode == COLOR_BIOME_RAW) c = biome_color(koppen[r], e);
+        else if (mode == COLOR_KOPPEN) c = koppen_class_color(koppen[r]);
         else if (mode == COLOR_HEIGHTMAP) { double t = (elev_to_height_km(e) + 5) / 11; t = t > 1 ? 1 : t; t = t < 0 ? 0 : t; c = {t, t, t}; }
         else if (mode == COLOR_LAND_HEIGHTMAP) { if (e > 0) { double t = elev_to_height_km(e) / 6; t = t > 1 ? 1 : t; t = t < 0 ? 0 : t; c = {t, t, t}; } }
         else if (e > 0) c = {1, 1, 1};

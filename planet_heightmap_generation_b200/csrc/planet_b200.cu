@@ -11,6 +11,7 @@
 #include "pb_coarse.h"
 #include "pb_climate.h"
 #include "pb_colors.h"
+#include "pb_export.h"
 #include <memory>
 #include <cxxabi.h>
 
@@ -53,6 +54,7 @@ struct pb_mesh {
     pb::DevBuf<float> sTriOut;
     pb::DevBuf<uint8_t> sMaskA, sMaskB, sMaskC;
     pb::DevBuf<float> sColorRaw;
+    std::unique_ptr<pb::MapExport> mapExport;
     pb::DevBuf<int> sPlateIO, sSuperIO;
     pb_mesh(pb::Context* c, int n, const int* o, const int* a, const float* x) : m(c, n, o, a, x) {}
 };
@@ -510,9 +512,9 @@ pb_status pb_classify_imported_regions(pb_mesh* mesh, const float* r_elevation, 
 pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation, const uint8_t* r_koppen, float* rgb) {
     return guard([&] {
         need(mesh && r_elevation && rgb, "NULL argument");
-        need(mode >= 0 && mode <= 5, "unknown colour mode");
-        const bool biome = mode == pb::COLOR_BIOME || mode == pb::COLOR_BIOME_RAW;
-        need(!biome || r_koppen, "biome colours need r_koppen");
+        need(mode >= 0 && mode <= 6, "unknown colour mode");
+        const bool biome = mode == pb::COLOR_BIOME || mode == pb::COLOR_BIOME_RAW || mode == pb::COLOR_KOPPEN;
+        need(!biome || r_koppen, "biome / koppen colours need r_koppen");
         pb::Mesh& m = mesh->m; m.ctx->bind();
         const size_t N = (size_t)m.N;
         const float* e = m.arg_in(r_elevation, N, m.sElev);
@@ -526,6 +528,38 @@ pb_status pb_region_colors(pb_mesh* mesh, int32_t mode, const float* r_elevation
             m.ex().for_each(m.N, pb::RegionColorK{mode, e, k, out});
         }
         m.arg_back(rgb, out, 3 * N);
+        m.finish();
+    });
+}
+
+// exportMap(type, width) js/planet-mesh.js:1752-1950 up to the ImageData: width × width/2 RGBA8 pixels, top row first
+pb_status pb_export_map(pb_mesh* mesh, int32_t colorMode, int32_t width, const float* r_elevation, const uint8_t* r_koppen,
+                        uint8_t* rgba, int32_t* pixelSide) {
+    return guard([&] {
+        need(mesh && r_elevation && rgba, "NULL argument");
+        need(colorMode >= 0 && colorMode <= 6 && colorMode != pb::COLOR_BIOME_RAW, "unknown export colour mode");
+        need(width >= 2 && width <= 65536 && width % 2 == 0, "width must be even, 2 … 65536");
+        const bool biome = colorMode == pb::COLOR_BIOME || colorMode == pb::COLOR_KOPPEN;
+        need(!biome || r_koppen, "biome / koppen exports need r_koppen");
+        pb::Mesh& m = mesh->m; m.ctx->bind();
+        if (!mesh->mapExport) mesh->mapExport.reset(new pb::MapExport());
+        pb::MapExport& X = *mesh->mapExport;
+        const size_t N = (size_t)m.N, px = (size_t)width * (size_t)(width / 2);
+        const float* e = m.arg_in(r_elevation, N, m.sElev);
+        const uint8_t* k = biome ? m.arg_in(r_koppen, N, mesh->sMaskA) : nullptr;
+        float* rgb = X.rgb.ensure(3 * N);
+        if (colorMode == pb::COLOR_BIOME) {
+            m.ex().for_each(m.N, pb::RegionColorK{colorMode, e, k, X.rgbRaw.ensure(3 * N)});
+            m.ex().for_each(m.N, pb::BiomeBlendK{m.csr(), X.rgbRaw.p, rgb});
+        } else {
+            m.ex().for_each(m.N, pb::RegionColorK{colorMode, e, k, rgb});
+        }
+        uint8_t* out = m.arg_out(rgba, 4 * px, X.sRgba);
+        int* side = pixelSide ? m.arg_out(pixelSide, px, X.sSide) : nullptr;
+        const bool bw = colorMode == pb::COLOR_HEIGHTMAP || colorMode == pb::COLOR_LAND_HEIGHTMAP || colorMode == pb::COLOR_LAND_MASK;
+        X.run(m, mesh->triangles, rgb, bw, width, out, side);
+        m.arg_back(rgba, out, 4 * px);
+        if (pixelSide) m.arg_back(pixelSide, side, px);
         m.finish();
     });
 }

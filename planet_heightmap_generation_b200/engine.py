@@ -222,11 +222,11 @@ class DeviceMesh:
             self._mesh, self._ptr(r_elevation, "f32", self.numRegions, "r_elevation"), self._ptr(out, "f32", self.numTriangles, "t_elevation")))
         return out
 
-    COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5}
+    COLOR_MODES = {"terrain": 0, "biome": 1, "heightmap": 2, "landheightmap": 3, "landmask": 4, "biomeRaw": 5, "koppen": 6}
 
     def regionColors(self, mode: str, r_elevation, r_koppen=None, out=None):
         """Per-region r,g,b (Float32, 3·numRegions) of one of the renderer's colour modes: elevationToColor, smoothBiomeColors /
-        biomeColor, heightmapColor, landHeightmapColor, landMaskColor (js/color-map.js:73-125, js/planet-mesh.js:30-80)."""
+        biomeColor, heightmapColor, landHeightmapColor, landMaskColor, koppenColor (js/color-map.js:73-125, js/planet-mesh.js:30-80, 175-178)."""
         n = self.numRegions
         if out is None:
             out = self._new(r_elevation, "f32", 3 * n)

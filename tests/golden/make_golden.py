@@ -51,6 +51,12 @@ def compute():
               "r_temperature_summer", "r_temperature_winter"):
         out["climate." + k] = sha(oc.get(k))
     out["climate.r_coastDistLand"] = sha(oc.get("r_coastDistLand", np.int32))
+    # equirectangular export of that planet (js/planet-mesh.js:1752-1950): owner side per pixel + RGBA, 256 x 128
+    koppen = oc.run_all(elev, pio, r_plate, 42)
+    for etype in ("colormap", "biome", "koppen", "heightmap", "landmask"):
+        px, side = oracle.export_map(mesh, xyz, etype, 256, elev, koppen)
+        out["export." + etype] = sha(px)
+    out["export.pixelSide"] = sha(side)
     # plate pipeline (coarse stage on a 4 000-region coarse mesh, projection, smoothing, super plates)
     cp = oracle.generate_coarse_plates(42, 24, 3, 0.5, 0.3, n_coarse=4000)
     out["plates.coarse_xyz"] = sha(cp["coarse_xyz"])

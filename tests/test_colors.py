@@ -7,7 +7,7 @@ from planet_heightmap_generation_b200.engine import DeviceMesh
 from tests.conftest import make_planet
 
 
-@pytest.mark.parametrize("mode", ["terrain", "biome", "biomeRaw", "heightmap", "landheightmap", "landmask"])
+@pytest.mark.parametrize("mode", ["terrain", "biome", "biomeRaw", "koppen", "heightmap", "landheightmap", "landmask"])
 def test_region_colors_match_oracle(backend, oracle, mode):
     mesh, xyz, nd, elev = make_planet(oracle, 6000)
     rng = np.random.default_rng(11)
@@ -20,7 +20,7 @@ def test_region_colors_match_oracle(backend, oracle, mode):
     elev[100:131] = 0.97          # snow / alpine zones for every class
     koppen[100:131] = np.arange(31)
     dm = DeviceMesh(mesh, xyz, lib=backend)
-    got = dm.regionColors(mode, elev, koppen if mode.startswith("biome") else None)
+    got = dm.regionColors(mode, elev, koppen if mode.startswith("biome") or mode == "koppen" else None)
     want = oracle.region_colors(mesh, mode, elev, koppen)
     assert got.dtype == np.float32 and got.shape == (3 * mesh.numRegions,)
     assert (got.view(np.uint32) == want.view(np.uint32)).all()

@@ -84,3 +84,21 @@ def test_climate_stack_large(cuda_lib, oracle):
     assert_bit_equal(wind["r_coastDistLand"], oc.get("r_coastDistLand", np.int32), "r_coastDistLand")
     assert_bit_equal(koppen, o_koppen, "r_koppen")
     assert len(np.unique(koppen)) >= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("etype", ["biome", "heightmap"])
+def test_export_map_large(cuda_lib, oracle, etype):
+    """exportMap (js/planet-mesh.js:1752-1950) of the eroded 250 001-cell planet at 2048 × 1024: ≈ 1.4 pixels per map triangle,
+    the regime of the reference's own exports; owner side per pixel and RGBA bytes against the oracle."""
+    from planet_heightmap_generation_b200 import planet_mesh as pm
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    c = _oracle_chain(oracle)
+    elev = c["eroded"]
+    koppen = (np.random.default_rng(3).integers(1, 31, elev.size) * (elev > 0)).astype(np.uint8)
+    dm = DeviceMesh(c["mesh"], c["xyz"], lib=cuda_lib)
+    got, got_side = pm.exportMapPixels(dm, etype, 2048, elev, koppen, want_sides=True)
+    want, want_side = oracle.export_map(c["mesh"], c["xyz"], etype, 2048, elev, koppen)
+    assert (got_side == want_side).all()
+    assert (got == want).all()
+    dm.close()
