@@ -77,6 +77,16 @@ class PlanetWorker:
             self.W["mesh"].close()
             self.W = None
 
+    def exportMap(self, curData: dict, type: str, width: int):
+        """exportMap(type, width) (js/planet-mesh.js:1752-1961).  In the reference this runs on the main thread over
+        `state.curData` — the last done / reapplyDone / editDone reply (its `r_elevation`, `debugLayers.koppen`, `seed`) — and
+        the mesh; here the mesh is the retained one in HBM.  → (download filename, PNG bytes)"""
+        from . import planet_mesh as pm
+        if self.W is None:
+            raise RuntimeError("No retained state for exportMap")
+        layers = curData.get("debugLayers") or {}
+        return pm.exportMap(self.W["mesh"], type, width, curData["r_elevation"], layers.get("koppen"), seed=curData.get("seed", ""))
+
     def _retain(self, new_state):
         """W = new_state once the run has succeeded (:277-292); the planet held before is released"""
         old, self.W = self.W, new_state

@@ -111,6 +111,13 @@ def test_worker_commands_match_the_reference_handlers(backend, oracle):
     e64 = elev.astype(np.float64)
     assert same(r["t_elevation"], (((e64[t[:, 0]] + e64[t[:, 1]]) + e64[t[:, 2]]) / 3).astype(np.float32))
     assert {"_pipelineTiming", "_postTiming", "_timing", "_params", "t_xyz", "mountain_r", "coastline_r", "ocean_r"} <= set(r)
+    # the main thread's exports of that reply (js/planet-mesh.js:1752): Satellite and Köppen maps as PNG
+    from planet_heightmap_generation_b200 import planet_mesh as pm
+    for etype, fname in (("biome", "orogen-satellite-%s.png"), ("koppen", "orogen-climate-%s.png")):
+        name, png = w.exportMap(r, etype, 256)
+        assert name == fname % r["seed"]
+        want_px, _ = oracle.export_map(ow.mesh, ow.xyz, etype, 256, elev, koppen)
+        assert (pm.decode_png(png) == want_px).all()
 
     # reapply with other sliders, climate skipped → cached wind dropped (:386-389)
     msg = dict(cmd="reapply", smoothing=0.3, glacialErosion=0.2, hydraulicErosion=0.7, thermalErosion=0.0, ridgeSharpening=0.2,
