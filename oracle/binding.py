@@ -356,12 +356,26 @@ def build_super_plates(mesh, r_plate, plates):
     return r_super, table
 
 
-def generate_coarse_plates(seed, num_plates, num_continents, continent_size_variety=0.0, land_coverage=0.3, n_coarse=20000):
+def build_sphere(n, jitter, seed, mesh_order="canonical"):
+    """buildSphere(N, jitter, makeRng(seed)) (js/sphere-mesh.js:174-186) → (SphereMesh, r_xyz).  mesh_order "canonical": qhull
+    triangulation under the documented canonical numbering (mesh_hull.py); "delaunator": the numbering of the reference's own
+    triangulator as restated in delaunator_ref.py (pure Python: seconds per 10 000 points)."""
+    xyz = fibonacci_sphere(n, jitter, seed)
+    if mesh_order == "canonical":
+        from .mesh_hull import build_sphere_from_points
+        return build_sphere_from_points(xyz)
+    from planet_heightmap_generation_b200.mesh import SphereMesh
+    from .delaunator_ref import build_sphere_delaunator
+    tri, half, _, _, _ = build_sphere_delaunator(xyz)
+    return SphereMesh(tri, half, n + 1), xyz
+
+
+def generate_coarse_plates(seed, num_plates, num_continents, continent_size_variety=0.0, land_coverage=0.3, n_coarse=20000,
+                           mesh_order="canonical"):
     """generateCoarsePlates (js/coarse-plates.js:19-39): coarse mesh of buildSphere(n_coarse, 0.75, makeRng(seed + 137)),
     generatePlates (js/plates.js:6-232) and assignOceanLand (js/ocean-land.js:7-238) on it.
     Returns dict(coarseMesh, coarse_xyz, coarse_r_plate, coarsePlateSeeds, coarsePlateVec, coarsePlateIsOcean)."""
-    from .mesh_hull import build_sphere_from_points
-    cmesh, cxyz = build_sphere_from_points(fibonacci_sphere(n_coarse, 0.75, seed + 137))
+    cmesh, cxyz = build_sphere(n_coarse, 0.75, seed + 137, mesh_order)
     n = cmesh.numRegions
     r_plate = np.empty(n, np.int32)
     seeds = np.zeros(num_plates, np.int32)

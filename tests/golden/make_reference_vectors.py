@@ -1,0 +1,160 @@
+"""Generates tests/golden/reference_*.npz by EXECUTING THE UNMODIFIED REFERENCE (/root/reference/js/planet-worker.js and every
+module it imports) under the minimal evaluator in tests/golden/minijs.py — the reference is browser JavaScript and this image
+has no JavaScript runtime.  Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_reference_vectors.py            # all scenarios, a few minutes
+
+What runs is the reference's own source, byte for byte: the worker's `self.onmessage` receives the same command objects the
+web app posts (generate, reapply, computeClimate, editRecompute, importHeightmap) and the messages it posts back are stored.
+Two things the reference pulls from outside its tree are supplied by the host, and the vectors inherit them:
+  * `delaunator@5.0.1` (CDN import, js/planet-worker.js:17) → oracle/delaunator_ref.py, a restatement of the published
+    algorithm.  Every array downstream of the mesh depends only on the reference's code GIVEN that triangulation;
+  * `Math.sin/cos/exp/pow/…` → Python's libm (V8 uses an fdlibm port; include/pb_detmath.h is a third implementation).
+tests/test_reference_vectors.py compares the oracle, the host emulation and (under -m gpu) the CUDA library with these files.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_JS = "/root/reference/js"
+CDN = "https://cdn.jsdelivr.net/npm/delaunator@5.0.1/+esm"
+
+SLIDERS = dict(smoothing=0.10, hydraulicErosion=0.50, thermalErosion=0.10, ridgeSharpening=0.50, glacialErosion=0.50, terrainWarp=0.75)
+
+SCENARIOS = {
+    # name: list of commands posted to one worker, in order
+    "A_600": [
+        dict(cmd="generate", N=600, P=12, jitter=0.75, nMag=0.4, numContinents=3, continentSizeVariety=0.0, seed=42, **SLIDERS),
+        dict(cmd="reapply", smoothing=0.3, glacialErosion=0.2, hydraulicErosion=0.7, thermalErosion=0.0, ridgeSharpening=0.2, terrainWarp=0.0,
+             skipClimate=True),
+        dict(cmd="computeClimate", temperatureOffset=2.5, precipitationOffset=-0.2),
+        dict(cmd="editRecompute", nMag=0.55, EDIT=True, **SLIDERS),
+    ],
+    "B_2500": [
+        dict(cmd="generate", N=2500, P=30, jitter=0.6, nMag=0.5, numContinents=4, continentSizeVariety=0.5, landCoverage=0.4,
+             temperatureOffset=-1.5, precipitationOffset=0.15, toggledIndices=[1, 4], seed=7, smoothing=0.25, hydraulicErosion=0.8,
+             thermalErosion=0.4, ridgeSharpening=0.3, glacialErosion=0.9, terrainWarp=0.4),
+    ],
+    "C_10000": [      # BASELINE config 1: 10k-cell sphere, default sliders
+        dict(cmd="generate", N=10000, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, **SLIDERS),
+    ],
+    "D_import_600": [
+        dict(cmd="importHeightmap", N=600, jitter=0.75, IMAGE=(64, 32), seed=11, **SLIDERS),
+    ],
+    "E_single_layer_400": [     # P < 8: no super plates (js/planet-worker.js:207), single-layer collisions
+        dict(cmd="generate", N=400, P=6, jitter=0.75, nMag=0.4, numContinents=2, continentSizeVariety=0.0, seed=3, **SLIDERS),
+    ],
+}
+# C keeps only the arrays BASELINE's configs name (the rest can be regenerated); the others keep every array of every reply
+KEEP_C = {"r_plate", "prePostElev", "r_elevation", "r_stress", "t_elevation", "r_wind_east_summer", "r_wind_north_winter",
+          "r_ocean_warmth_summer", "r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter",
+          "debugLayers.erosionDelta", "debugLayers.koppen", "debugLayers.hotspot", "debugLayers.superPlates"}
+
+
+def synthetic_image(w, h):
+    yy, xx = np.mgrid[0:h, 0:w]
+    g = 96 + 70 * np.sin(xx * 0.31) * np.cos(yy * 0.23) + 50 * np.sin((xx + 2 * yy) * 0.11)
+    return np.clip(g, 0, 255).astype(np.uint8).ravel()
+
+
+def make_interpreter():
+    from oracle.delaunator_ref import delaunator
+    from tests.golden import minijs as js
+
+    def delaunator_ctor(args):
+        flat = js.to_python(args[0])
+        tri, half = delaunator(flat.tolist())
+        o = js.JSObject()
+        o.props["coords"] = args[0]
+        o.props["triangles"] = js.from_python(np.asarray(tri, np.uint32))
+        o.props["halfedges"] = js.from_python(np.asarray(half, np.int32))
+        return o
+    D = js.HostFunction(lambda this, args: js.throw_error("TypeError", "Class constructor Delaunator cannot be invoked without 'new'"),
+                        "Delaunator", delaunator_ctor)
+    it = js.Interpreter(REFERENCE_JS, host_modules={CDN: {"default": D}})
+    posted = []
+    worker_self = js.JSObject()
+    worker_self.props["postMessage"] = js.HostFunction(lambda this, args: (posted.append(js.to_python(args[0])), js.UNDEF)[1], "postMessage")
+    it.globals["self"] = worker_self
+    it.load("planet-worker.js")
+
+    def post(message: dict):
+        del posted[:]
+        ev = js.JSObject(None, {"data": js.from_python(message)})
+        js.call_function(worker_self.props["onmessage"], worker_self, [ev])
+        replies = [m for m in posted if m.get("type") != "progress"]
+        if len(replies) != 1:
+            raise RuntimeError(f"expected one reply, got {[m.get('type') for m in replies]}")
+        if replies[0]["type"] == "error":
+            raise RuntimeError(f"the reference worker posted an error: {replies[0]['message']}")
+        return replies[0]
+    return post
+
+
+def flatten(reply: dict):
+    """(arrays, meta): numpy arrays by dotted key; everything else JSON-able"""
+    arrays, meta = {}, {}
+    for k, v in reply.items():
+        if isinstance(v, np.ndarray):
+            arrays[k] = v
+        elif k in ("debugLayers", "windDebugLayers") and isinstance(v, dict):
+            for kk, vv in v.items():
+                if isinstance(vv, np.ndarray):
+                    arrays[f"{k}.{kk}"] = vv
+        elif k.startswith("_"):
+            continue            # timings
+        else:
+            meta[k] = v
+    return arrays, meta
+
+
+def run_scenario(name):
+    post = make_interpreter()
+    out, metas, commands = {}, [], []
+    last_done = None
+    for i, cmd in enumerate(SCENARIOS[name]):
+        cmd = dict(cmd)
+        if cmd.pop("EDIT", False):
+            # what the edit UI sends (js/edit-mode.js): the current ocean set with one plate toggled and one density changed
+            seeds = [int(s) for s in last_done["plateSeeds"]]
+            ocean = {int(s) for s in last_done["plateIsOcean"]}
+            ocean ^= {seeds[2]}
+            dens = {str(int(k)): float(v) for k, v in last_done["plateDensity"].items()}
+            dens[str(seeds[0])] = 2.95
+            cmd.update(plateIsOcean=sorted(ocean), plateDensity=dens)
+        if "IMAGE" in cmd:
+            w, h = cmd.pop("IMAGE")
+            cmd.update(grayscale=synthetic_image(w, h), imageWidth=w, imageHeight=h)
+        t0 = time.time()
+        reply = post(cmd)
+        print(f"  {name}[{i}] {cmd['cmd']}: {reply['type']} in {time.time() - t0:.1f} s", flush=True)
+        if reply["type"] == "done":
+            last_done = reply
+        arrays, meta = flatten(reply)
+        if name.startswith("C_"):
+            arrays = {k: v for k, v in arrays.items() if k in KEEP_C}
+        for k, v in arrays.items():
+            out[f"{i}/{k}"] = v
+        metas.append(meta)
+        commands.append({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in cmd.items()})
+    out["__meta__"] = np.frombuffer(json.dumps({"commands": commands, "replies": metas}, default=lambda o: o.tolist()).encode(), np.uint8)
+    path = os.path.join(HERE, f"reference_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out) - 1} arrays)")
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REFERENCE_JS):
+        sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
+    names = sys.argv[1:] or list(SCENARIOS)
+    for n in names:
+        print(n, flush=True)
+        run_scenario(n)

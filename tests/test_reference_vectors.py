@@ -1,0 +1,155 @@
+"""Parity against THE REFERENCE ITSELF.  tests/golden/reference_*.npz hold the replies of the unmodified reference worker
+(/root/reference/js/planet-worker.js + every module it imports) to the web app's own commands — generate, reapply,
+computeClimate, editRecompute, importHeightmap — produced in the build container by executing that source under the
+minimal ECMAScript evaluator tests/golden/minijs.py (tests/golden/make_reference_vectors.py; the image has no JavaScript
+runtime).  The same commands are replayed here through
+
+  * the engine's worker mirror in the reference's neighbour order (`mesh_order="delaunator"`): host emulation of the kernels in the
+    CPU suite, the CUDA library under -m gpu, and
+  * the oracle's restatement of the handlers (tests/test_worker.py:OracleWorker),
+
+and every array of every reply is compared: integer fields (triangles, halfedges, r_plate, Köppen classes, region sets) must be
+identical, and so must the Float32 fields — bit for bit, up to the one evaluation in ~1e8 where the third `Math.*`
+implementation involved (Python's libm for the vectors, include/pb_detmath.h here, V8's fdlibm port in a browser) rounds a
+Float32 store the other way; the hard limit is BASELINE's 1e-4 relative.  Inherited by the vectors: the triangulation comes from
+oracle/delaunator_ref.py (delaunator@5.0.1 is a CDN import of the reference, not part of its tree)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from planet_heightmap_generation_b200.worker import PlanetWorker
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SCENARIOS = ["A_600", "B_2500", "C_10000", "D_import_600", "E_single_layer_400"]
+SET_KEYS = ("mountain_r", "coastline_r", "ocean_r")
+REL_TOL = 1e-4            # BASELINE north_star: "float elevation/climate within 1e-4 relative"
+MAX_ULP_FLIPS = 2         # Float32 elements per array allowed to differ at all (see the module docstring)
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, f"reference_{name}.npz"))
+    meta = json.loads(bytes(z["__meta__"]).decode())
+    replies = []
+    for i, rmeta in enumerate(meta["replies"]):
+        arrays = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(f"{i}/")}
+        replies.append((rmeta, arrays))
+    return meta["commands"], replies
+
+
+def command_for(cmd):
+    c = dict(cmd)
+    if "grayscale" in c:
+        c["grayscale"] = np.asarray(c["grayscale"], np.uint8)
+    if "plateDensity" in c:
+        c["plateDensity"] = {int(k): v for k, v in c["plateDensity"].items()}
+    return c
+
+
+def lookup(reply, dotted):
+    v = reply
+    for part in dotted.split("."):
+        if v is None:
+            return None
+        v = v.get(part)
+    return v
+
+
+def check_array(where, got, want, stats):
+    assert got is not None, f"{where}: missing in the reply"
+    got = np.asarray(got)
+    assert got.shape == want.shape, f"{where}: shape {got.shape} vs reference {want.shape}"
+    if want.dtype.kind == "f":
+        g, w = got.astype(np.float32), want.astype(np.float32)
+        differ = (g.view(np.uint32) != w.view(np.uint32)) & ~((g == 0) & (w == 0))
+        n = int(differ.sum())
+        stats["float_elements"] += g.size
+        stats["float_differing"] += n
+        if n:
+            rel = float(np.max(np.abs(g[differ].astype(np.float64) - w[differ]) / np.maximum(np.abs(w[differ]), 1e-3)))
+            stats["worst"] = max(stats["worst"], rel)
+            assert rel <= REL_TOL, f"{where}: {n} of {g.size} differ, worst relative {rel:.3g}"
+            assert n <= MAX_ULP_FLIPS, f"{where}: {n} of {g.size} Float32 values differ from the reference (allowed {MAX_ULP_FLIPS})"
+    else:
+        bad = got.astype(np.int64) != want.astype(np.int64)
+        stats["int_elements"] += got.size
+        assert not bad.any(), f"{where}: {int(bad.sum())} of {got.size} integer values differ from the reference"
+
+
+def check_reply(name, i, reply, rmeta, arrays, stats):
+    assert reply["type"] == rmeta["type"], f"{name}[{i}]: {reply}"
+    for key, want in arrays.items():
+        check_array(f"{name}[{i}].{key}", lookup(reply, key), want, stats)
+    for key in SET_KEYS:
+        if key in rmeta:
+            assert sorted(int(r) for r in reply[key]) == sorted(int(r) for r in rmeta[key]), f"{name}[{i}].{key}"
+    if "plateSeeds" in rmeta:
+        assert [int(s) for s in reply["plateSeeds"]] == [int(s) for s in rmeta["plateSeeds"]], "plateSeeds (Set order)"
+        assert sorted(int(s) for s in reply["plateIsOcean"]) == sorted(int(s) for s in rmeta["plateIsOcean"]), "plateIsOcean"
+    for key in ("plateDensity", "plateDensityLand", "plateDensityOcean"):
+        if rmeta.get(key):
+            assert {int(k): v for k, v in reply[key].items()} == {int(k): v for k, v in rmeta[key].items()}, key
+    if rmeta.get("plateVec"):
+        # Euler poles are doubles computed with sin / cos / acos: the three Math implementations differ in the last ulp of a double
+        for pid, pv in rmeta["plateVec"].items():
+            mine = reply["plateVec"][int(pid)]
+            if isinstance(pv, dict):
+                assert np.allclose(mine["pole"], pv["pole"], rtol=1e-13, atol=1e-15) and abs(mine["omega"] - pv["omega"]) <= 1e-13 * abs(pv["omega"]), f"plateVec[{pid}]"
+            else:                         # importHeightmap posts zero vectors (js/planet-worker.js:838-840)
+                assert list(mine if not isinstance(mine, dict) else mine["pole"]) == list(pv), f"plateVec[{pid}]"
+    for key in ("numRegions", "seed", "nMag", "skipClimate"):
+        if key in rmeta:
+            assert reply[key] == rmeta[key], key
+
+
+def test_vectors_are_complete():
+    for name in SCENARIOS:
+        commands, replies = load(name)
+        assert len(commands) == len(replies) >= 1
+        assert all(r[0]["type"] in ("done", "reapplyDone", "climateDone", "editDone") for r in replies)
+    commands, replies = load("A_600")
+    assert [c["cmd"] for c in commands] == ["generate", "reapply", "computeClimate", "editRecompute"]
+    assert len(replies[0][1]) >= 50 and replies[0][1]["r_elevation"].size == 601
+    assert {"triangles", "halfedges", "r_xyz", "t_xyz", "r_plate", "prePostElev", "r_elevation", "r_stress", "debugLayers.koppen"} <= set(replies[0][1])
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_engine_replays_the_reference_worker(backend, name):
+    commands, replies = load(name)
+    w = PlanetWorker(lib=backend, mesh_order="delaunator")
+    stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
+    for i, (cmd, (rmeta, arrays)) in enumerate(zip(commands, replies)):
+        reply = w.onmessage(command_for(cmd))
+        check_reply(name, i, reply, rmeta, arrays, stats)
+    w.close()
+    assert stats["float_elements"] > 5000 and stats["int_elements"] > 400
+    print(f"{name}: {stats}")
+
+
+@pytest.mark.parametrize("name", ["A_600", "B_2500", "E_single_layer_400"])
+def test_oracle_replays_the_reference_worker(oracle, name):
+    """The oracle's handlers (the checker every other parity test trusts) against the reference's own replies."""
+    from tests.test_worker import OracleWorker
+    commands, replies = load(name)
+    ow = OracleWorker(oracle, mesh_order="delaunator")
+    stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
+    cmd, (rmeta, ref) = commands[0], replies[0]
+    elev, delta, koppen = ow.generate(cmd)
+    got = {"r_xyz": ow.xyz, "triangles": ow.mesh.triangles, "halfedges": ow.mesh.halfedges, "r_plate": ow.r_plate, "prePostElev": ow.pre,
+           "r_elevation": elev, "r_stress": ow.oe.get("r_stress"), "t_xyz": oracle.triangle_centers(ow.mesh, ow.xyz),
+           "debugLayers.erosionDelta": delta, "debugLayers.koppen": koppen}
+    for k in ("base", "tectonic", "noise", "interior", "coastal", "ocean", "hotspot", "tecActivity", "margins", "backArc", "foldRidge", "orogenicPower"):
+        got["debugLayers." + k] = ow.oe.get(k)
+    for k in ("r_wind_east_summer", "r_wind_north_summer", "r_wind_east_winter", "r_wind_north_winter", "itczLons", "itczLatsSummer",
+              "itczLatsWinter", "r_ocean_current_east_summer", "r_ocean_current_north_winter", "r_ocean_speed_summer", "r_ocean_speed_winter",
+              "r_ocean_warmth_summer", "r_ocean_warmth_winter", "r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter"):
+        got[k] = ow.clim.get(k)
+    for k, v in got.items():
+        check_array(f"oracle {name}.{k}", v, ref[k], stats)
+    assert [int(s) for s in rmeta["plateSeeds"]] == ow.seeds
+    assert sorted(int(s) for s in rmeta["plateIsOcean"]) == sorted(ow.pio)
+    assert {int(k): v for k, v in rmeta["plateDensity"].items()} == ow.dens
+    for key in SET_KEYS:
+        assert sorted(int(r) for r in rmeta[key]) == [int(r) for r in np.nonzero(ow.oe.get(key, np.uint8))[0]], key
+    print(f"oracle {name}: {stats}")

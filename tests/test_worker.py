@@ -24,8 +24,9 @@ def same(a, b):
 class OracleWorker:
     """The handlers of js/planet-worker.js restated over oracle/ (test infrastructure)."""
 
-    def __init__(self, oracle):
+    def __init__(self, oracle, mesh_order="canonical"):
         self.o = oracle
+        self.mesh_order = mesh_order          # "delaunator": the reference's own neighbour order (oracle/delaunator_ref.py)
 
     def climate(self, elev, t_off, p_off, cover, recompute_wind=True):
         c = self.clim
@@ -44,12 +45,12 @@ class OracleWorker:
         return self.oe.get("r_elevation")
 
     def generate(self, d):
-        from oracle.mesh_hull import build_sphere_from_points
         o = self.o
         self.seed, self.P = d["seed"], d["P"]
-        self.mesh, self.xyz = build_sphere_from_points(o.fibonacci_sphere(d["N"], d["jitter"], self.seed))
+        self.mesh, self.xyz = o.build_sphere(d["N"], d["jitter"], self.seed, self.mesh_order)
         self.nd = o.neighbor_dist(self.mesh, self.xyz)
-        cp = o.generate_coarse_plates(self.seed, d["P"], d["numContinents"], d["continentSizeVariety"], d["landCoverage"])
+        cp = o.generate_coarse_plates(self.seed, d["P"], d["numContinents"], d.get("continentSizeVariety", 0.0), d.get("landCoverage", 0.3),
+                                      mesh_order=self.mesh_order)
         self.r_plate = o.project_coarse_plates(self.mesh, self.xyz, cp["coarseMesh"], cp["coarse_xyz"], cp["coarse_r_plate"], self.seed, d["P"])
         self.seeds, self.vec = cp["coarsePlateSeeds"], cp["coarsePlateVec"]
         o.smooth_and_reconnect_plates(self.mesh, self.r_plate, self.seeds, 3)
@@ -66,7 +67,7 @@ class OracleWorker:
         self.pre = elev.copy()
         delta, _ = o.run_post_processing(self.mesh, self.xyz, elev, {k: d[k] for k in SLIDER_KEYS}, self.nd, self.seed, self.oe.get("hotspot"))
         self.final = elev.copy()
-        koppen = self.climate(elev, d["temperatureOffset"], d["precipitationOffset"], d["landCoverage"])
+        koppen = self.climate(elev, d.get("temperatureOffset", 0.0), d.get("precipitationOffset", 0.0), d.get("landCoverage", 0.3))
         return elev, delta, koppen
 
     def reapply(self, d, t_off, p_off, cover):
