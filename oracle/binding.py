@@ -448,3 +448,17 @@ def export_map(mesh, xyz, export_type, width, elev, koppen=None):
                          _p(np.ascontiguousarray(xyz, np.float32), C.c_float), C.c_int(EXPORT_TYPES[export_type]), C.c_int(width),
                          _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(k, C.c_uint8), _p(rgba, C.c_uint8), _p(side, C.c_int32))
     return rgba, side
+
+
+def export_map_triangles(mesh, xyz, export_type, elev, koppen=None):
+    """(posArr float32[9 * triCount], colArr float32[9 * triCount]) of exportMap's triangle loop (js/planet-mesh.js:1766-1846)"""
+    pos = np.zeros(18 * mesh.numSides, np.float32)
+    col = np.zeros(18 * mesh.numSides, np.float32)
+    side = np.zeros(2 * mesh.numSides, np.int32)
+    k = np.zeros(mesh.numRegions, np.uint8) if koppen is None else np.ascontiguousarray(koppen, np.uint8)
+    lib().orc_export_map_triangles.restype = C.c_int
+    n = lib().orc_export_map_triangles(*_mesh_args(mesh), C.c_int(mesh.numSides), _p(mesh.triangles, C.c_int32), _p(mesh.halfedges, C.c_int32),
+                                       _p(np.ascontiguousarray(xyz, np.float32), C.c_float), C.c_int(EXPORT_TYPES[export_type]),
+                                       _p(np.ascontiguousarray(elev, np.float32), C.c_float), _p(k, C.c_uint8), _p(pos, C.c_float), _p(col, C.c_float),
+                                       _p(side, C.c_int32))
+    return pos[:9 * n].copy(), col[:9 * n].copy()

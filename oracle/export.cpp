@@ -78,20 +78,17 @@ void orc_triangle_centers(int numTriangles, const int32_t* triangles, const floa
     }
 }
 
-// colorMode as orc_region_colors (0 colormap, 1 biome = Satellite, 2 heightmap, 3 landheightmap, 4 landmask, 6 koppen)
-void orc_export_map(int N, const int32_t* off, const int32_t* adj, int numSides, const int32_t* triangles, const int32_t* halfedges,
-                    const float* r_xyz, int colorMode, int width, const float* r_elevation, const uint8_t* r_koppen,
-                    uint8_t* rgba, int32_t* pixelSide) {
-    const int height = width / 2;
-    const bool isBW = colorMode == 2 || colorMode == 3 || colorMode == 4;
+// the triangle stage of exportMap (:1766-1846): Float32 position / colour buffers (9 floats per triangle, capacity 2 * numSides
+// triangles) and, per triangle, the side it came from; returns triCount
+int orc_export_map_triangles(int N, const int32_t* off, const int32_t* adj, int numSides, const int32_t* triangles, const int32_t* halfedges,
+                             const float* r_xyz, int colorMode, const float* r_elevation, const uint8_t* r_koppen,
+                             float* posArr, float* colArr, int32_t* triSide) {
     const int numTriangles = numSides / 3;
     std::vector<float> t_xyz(3 * (size_t)numTriangles), regionColor(3 * (size_t)N);
     orc_triangle_centers(numTriangles, triangles, r_xyz, t_xyz.data());
     orc_region_colors(N, off, adj, colorMode, r_elevation, r_koppen, regionColor.data());
 
     const double PI = PB_PI, sx = 2 / PI;
-    std::vector<float> posArr((size_t)numSides * 18), colArr((size_t)numSides * 18);
-    std::vector<int32_t> triSide((size_t)numSides * 2);
     size_t triCount = 0;
     auto clx = [](double v) { return js::max(-2, js::min(2, v)); };
     auto cly = [](double v) { return js::max(-1, js::min(1, v)); };
@@ -125,6 +122,19 @@ void orc_export_map(int N, const int32_t* off, const int32_t* adj, int numSides,
             emit(lon0, lon1, lon2);
         }
     }
+    return (int)triCount;
+}
+
+// colorMode as orc_region_colors (0 colormap, 1 biome = Satellite, 2 heightmap, 3 landheightmap, 4 landmask, 6 koppen)
+void orc_export_map(int N, const int32_t* off, const int32_t* adj, int numSides, const int32_t* triangles, const int32_t* halfedges,
+                    const float* r_xyz, int colorMode, int width, const float* r_elevation, const uint8_t* r_koppen,
+                    uint8_t* rgba, int32_t* pixelSide) {
+    const int height = width / 2;
+    const bool isBW = colorMode == 2 || colorMode == 3 || colorMode == 4;
+    std::vector<float> posArr((size_t)numSides * 18), colArr((size_t)numSides * 18);
+    std::vector<int32_t> triSide((size_t)numSides * 2);
+    const size_t triCount = (size_t)orc_export_map_triangles(N, off, adj, numSides, triangles, halfedges, r_xyz, colorMode, r_elevation, r_koppen,
+                                                             posArr.data(), colArr.data(), triSide.data());
 
     Framebuffer fb{width, height, std::vector<uint8_t>(3 * (size_t)width * height), std::vector<int32_t>((size_t)width * height)};
     if (isBW) fb.clear(0, 0, 0);

@@ -80,6 +80,7 @@ def make_interpreter():
     D = js.HostFunction(lambda this, args: js.throw_error("TypeError", "Class constructor Delaunator cannot be invoked without 'new'"),
                         "Delaunator", delaunator_ctor)
     it = js.Interpreter(REFERENCE_JS, host_modules={CDN: {"default": D}})
+    _LAST["interp"] = it
     posted = []
     worker_self = js.JSObject()
     worker_self.props["postMessage"] = js.HostFunction(lambda this, args: (posted.append(js.to_python(args[0])), js.UNDEF)[1], "postMessage")
@@ -151,10 +152,71 @@ def run_scenario(name):
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out) - 1} arrays)")
 
 
+def _extract(src: str, start: str, end: str) -> str:
+    a = src.index(start)
+    return src[a:src.index(end, a)]
+
+
+def run_render_scenario():
+    """F_render_600: the pure pieces of js/planet-mesh.js — smoothBiomeColors, heightmapColor, landHeightmapColor, landMaskColor,
+    koppenColor and the triangle loop of exportMap (:1766-1846) — evaluated on the planet of scenario A.  planet-mesh.js itself
+    cannot be loaded (it imports three.js and the DOM-bound scene), so the text of those functions is cut out of the reference
+    file HERE, at generation time, and evaluated as a module next to it; nothing of it is stored in the repository."""
+    from tests.golden import minijs as js
+    post = make_interpreter()
+    reply = post(dict(SCENARIOS["A_600"][0]))
+    interp = _LAST["interp"]          # the interpreter make_interpreter() just built
+    worker = interp.modules[os.path.realpath(os.path.join(REFERENCE_JS, "planet-worker.js"))]
+    W = worker.env.v["W"]
+    pm = open(os.path.join(REFERENCE_JS, "planet-mesh.js"), encoding="utf-8").read()
+    body = _extract(pm, "function smoothBiomeColors(", "// Grayscale heightmap")
+    body += _extract(pm, "function heightmapColor(", "// Diverging color map")
+    body += _extract(pm, "function koppenColor(", "// Plate colours")
+    export_map = pm[pm.index("export async function exportMap("):]
+    loop = _extract(export_map, "    const { numSides } = mesh;\n    const PI = Math.PI;", "    const geo = new THREE.BufferGeometry();")
+    module = ("import { elevationToColor, elevToHeightKm, biomeColor } from './color-map.js';\n"
+              "import { KOPPEN_CLASSES } from './koppen.js';\n" + body +
+              "function mapTriangles(mesh, r_xyz, t_xyz, r_elevation, type, koppenArr, biomeSmoothed) {\n" + loop +
+              "    return { posArr, colArr, triCount };\n}\n"
+              "export { smoothBiomeColors, heightmapColor, landHeightmapColor, landMaskColor, koppenColor, mapTriangles, elevationToColor };\n")
+    mod = interp.load(os.path.join(REFERENCE_JS, "__planet_mesh_extract__.js"), source=module)
+    fn = lambda n: mod.env.v[mod.exports[n]]          # noqa: E731
+    mesh, r_xyz = js.get_prop(W, "mesh"), js.get_prop(W, "r_xyz")
+    elev = js.from_python(reply["r_elevation"])
+    koppen = js.from_python(reply["debugLayers"]["koppen"])
+    t_xyz = js.from_python(reply["t_xyz"])
+    n = reply["r_elevation"].size
+    out = {}
+    smoothed = js.call_function(fn("smoothBiomeColors"), js.UNDEF, [mesh, koppen, elev])
+    out["colors.biome"] = js.to_python(smoothed)
+    for mode, name in (("terrain", "elevationToColor"), ("heightmap", "heightmapColor"), ("landheightmap", "landHeightmapColor"), ("landmask", "landMaskColor")):
+        rgb = np.empty(3 * n, np.float32)
+        for r in range(n):
+            rgb[3 * r:3 * r + 3] = js.to_python(js.call_function(fn(name), js.UNDEF, [float(reply["r_elevation"][r])]))
+        out["colors." + mode] = rgb
+    ids = list(range(0, 33)) + [200]
+    out["koppenColor.ids"] = np.asarray(ids, np.int32)
+    out["koppenColor.rgb"] = np.asarray([js.to_python(js.call_function(fn("koppenColor"), js.UNDEF, [float(i)])) for i in ids], np.float64).ravel()
+    for etype in ("biome", "heightmap", "colormap", "koppen"):
+        res = js.call_function(fn("mapTriangles"), js.UNDEF, [mesh, r_xyz, t_xyz, elev, etype, koppen, smoothed])
+        cnt = int(js.get_prop(res, "triCount"))
+        out[f"triangles.{etype}.pos"] = js.to_python(js.get_prop(res, "posArr"))[:9 * cnt]
+        out[f"triangles.{etype}.col"] = js.to_python(js.get_prop(res, "colArr"))[:9 * cnt]
+    path = os.path.join(HERE, "reference_F_render_600.npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out)} arrays)")
+
+
+_LAST = {}
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE_JS):
         sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
-    names = sys.argv[1:] or list(SCENARIOS)
+    names = sys.argv[1:] or list(SCENARIOS) + ["F_render_600"]
     for n in names:
         print(n, flush=True)
-        run_scenario(n)
+        if n == "F_render_600":
+            run_render_scenario()
+        else:
+            run_scenario(n)

@@ -2711,12 +2711,13 @@ class Interpreter:
     def host_function(self, fn, name=""):
         return HostFunction(fn, name)
 
-    def load(self, path: str) -> Module:
+    def load(self, path: str, source: str | None = None) -> Module:
+        """evaluates a module once; `source` supplies the text for a virtual path (relative imports resolve against that path)"""
         path = os.path.realpath(os.path.join(self.root, path)) if not os.path.isabs(path) else os.path.realpath(path)
         if path in self.modules:
             return self.modules[path]
         mod = self.modules[path] = Module(path)
-        src = open(path, encoding="utf-8").read()
+        src = source if source is not None else open(path, encoding="utf-8").read()
         ast = parse(src, path)
         body = ast[1]
         scope = CScope(None, True)

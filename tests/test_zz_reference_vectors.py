@@ -153,3 +153,48 @@ def test_oracle_replays_the_reference_worker(oracle, name):
     for key in SET_KEYS:
         assert sorted(int(r) for r in rmeta[key]) == [int(r) for r in np.nonzero(ow.oe.get(key, np.uint8))[0]], key
     print(f"oracle {name}: {stats}")
+
+
+def _planet_A():
+    """mesh, r_xyz and the final arrays of scenario A's generate reply"""
+    from planet_heightmap_generation_b200.mesh import SphereMesh
+    _, replies = load("A_600")
+    ref = replies[0][1]
+    mesh = SphereMesh(ref["triangles"], ref["halfedges"], int(replies[0][0]["numRegions"]))
+    return mesh, ref["r_xyz"], ref["r_elevation"], ref["debugLayers.koppen"]
+
+
+def test_colour_ramps_match_the_reference(backend, oracle):
+    """elevationToColor (js/color-map.js:116-125), smoothBiomeColors over biomeColor, heightmapColor, landHeightmapColor,
+    landMaskColor, koppenColor (js/planet-mesh.js:30-80, 175-178) evaluated from the reference's source: Float32 colour buffers."""
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    z = np.load(os.path.join(GOLDEN, "reference_F_render_600.npz"))
+    mesh, xyz, elev, koppen = _planet_A()
+    dm = DeviceMesh(mesh, xyz, lib=backend)
+    stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
+    for mode in ("terrain", "biome", "heightmap", "landheightmap", "landmask"):
+        want = z["colors." + mode]
+        check_array(f"oracle colours {mode}", oracle.region_colors(mesh, mode, elev, koppen), want, stats)
+        check_array(f"engine colours {mode}", dm.regionColors(mode, elev, koppen if mode == "biome" else None), want, stats)
+    ids = z["koppenColor.ids"]
+    k = np.zeros(mesh.numRegions, np.uint8)
+    k[:ids.size] = ids.astype(np.uint8)
+    want = z["koppenColor.rgb"].astype(np.float32)
+    check_array("oracle koppenColor", oracle.region_colors(mesh, "koppen", elev, k)[:3 * ids.size], want, stats)
+    check_array("engine koppenColor", dm.regionColors("koppen", elev, k)[:3 * ids.size], want, stats)
+    assert stats["float_differing"] == 0
+    dm.close()
+
+
+@pytest.mark.parametrize("etype", ["biome", "heightmap", "colormap", "koppen"])
+def test_export_triangles_match_the_reference(oracle, etype):
+    """The triangle loop of exportMap (js/planet-mesh.js:1766-1846) run from the reference's source on scenario A's planet: the
+    Float32 position and colour buffers of the oracle's export (the pixels of the engine are compared with the oracle's in
+    tests/test_export_map.py; the rasteriser between the two is WebGL in the reference, a stated rule here)."""
+    z = np.load(os.path.join(GOLDEN, "reference_F_render_600.npz"))
+    mesh, xyz, elev, koppen = _planet_A()
+    pos, col = oracle.export_map_triangles(mesh, xyz, etype, elev, koppen)
+    stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
+    check_array(f"posArr {etype}", pos, z[f"triangles.{etype}.pos"], stats)
+    check_array(f"colArr {etype}", col, z[f"triangles.{etype}.col"], stats)
+    assert stats["float_differing"] == 0 and stats["float_elements"] > 60000
