@@ -1,6 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  "Parity unpinned": the reference has no
-// tests, no golden vectors and cannot run in this image (no JS runtime); this file restates its
-// source line by line.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  The reference has no tests or golden
+// vectors and no JS runtime exists in this image; this file restates its source line by line and is pinned against that source
+// executed under tests/golden/minijs.py (tests/test_zz_reference_vectors.py: every climate array of every reply, bit for bit).
 //
 // CPU restatement of the reference's climate stack, single thread, double arithmetic with f32
 // typed-array stores, same loop order:

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Parity unpinned (no reference vectors exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Pinned against the reference's own source run under tests/golden/minijs.py (tests/test_zz_reference_vectors.py).
 // Sequential restatement of the coarse stage that feeds the plate pipeline:
 //   generatePlates     js/plates.js:6-232      (farthest-point seeds, round-robin weighted growth, Euler poles)
 //   assignOceanLand    js/ocean-land.js:7-238  (continent seeding / growth on the plate graph, trapped seas)

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Parity unpinned (no reference vectors exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Pinned against the reference's own source run under tests/golden/minijs.py (scenario F_render_600).
 // Per-region colour ramps of the render / export side:
 //   elevToHeightKm, biomeColor, elevationToColor   js/color-map.js:7-12, 73-125
 //   smoothBiomeColors, heightmapColor, landHeightmapColor, landMaskColor   js/planet-mesh.js:30-80

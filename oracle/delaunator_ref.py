@@ -6,8 +6,9 @@ by the reference's own stereographicProjection / addPoleToMesh / SphereMesh cons
 Written independently of the engine's C++ (exact orientation sign through rational arithmetic instead of floating-point
 expansions) and only used by tests, on small inputs (pure Python loops).
 
-PARITY UNPINNED: neither the library nor a JavaScript runtime exists in this image, so the triangle numbering produced here
-cannot be compared with the original's output; it follows the published source (index.js of the 5.0.1 tag) from memory.
+PARITY UNPINNED for the numbering: the library is a CDN import of the reference (not in its tree), so the triangle numbering
+produced here cannot be compared with the original's output; it follows the published source (index.js of the 5.0.1 tag) from
+memory.  The reference vectors (tests/golden/make_reference_vectors.py) hand THIS triangulator to the reference's buildSphere.
 """
 from __future__ import annotations
 

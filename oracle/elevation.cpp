@@ -1,5 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  "Parity unpinned": the reference has no
-// tests or golden vectors and cannot run in this image; this file restates js/elevation.js line by line.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  The reference has no tests or golden
+// vectors and no JS runtime exists in this image; this file restates js/elevation.js line by line and is pinned against that
+// source executed under tests/golden/minijs.py (tests/test_zz_reference_vectors.py: elevation, stress, sets, debug layers).
 //
 //   plateVelocityAt :11-21, findCollisions :27-122, propagateStress :127-159,
 //   assignDistanceField :164-189, assignElevation :216-1391

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Parity unpinned (no reference vectors exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Triangle stage pinned against the reference's own loop run under tests/golden/minijs.py (scenario F_render_600); the framebuffer rule is this repository's.
 // exportMap(type, width), js/planet-mesh.js:1752-1950, restated up to the ImageData that is put on the canvas:
 //   :1773-1846  one map triangle per side (two when it straddles the date line) into Float32 posArr / colArr
 //   :1848-1895  THREE.Mesh with MeshBasicMaterial({vertexColors, DoubleSide}) rendered through orthographic tiles

@@ -5,8 +5,11 @@
 // JS-semantics helpers used by the CPU restatement of the reference
 // (raguilar011095/planet_heightmap_generation, js/*.js).  Parity status: the
 // reference ships no tests or golden vectors and no JS runtime exists in this
-// image, so the oracle is pinned only against the derived known-answer vectors in
-// SURVEY.md §8(c) (tests/test_oracle_kat.py) — "parity unpinned" by the reference.
+// image.  The oracle is pinned (a) against the derived known-answer vectors in
+// SURVEY.md §8(c) (tests/test_oracle_kat.py) and (b) against the reference's own
+// source executed under the minimal evaluator tests/golden/minijs.py: whole worker
+// replies committed under tests/golden/reference_*.npz and reproduced bit for bit
+// (tests/test_zz_reference_vectors.py; DESIGN.md §3 lists what that pin inherits).
 #pragma once
 #include <cmath>
 #include <cstdint>

@@ -6,8 +6,8 @@ unit vectors.  Delaunator is not part of the reference tree and no JS runtime ex
 qhull (scipy.spatial.ConvexHull) on the f64-normalised points.  Triangle numbering — and therefore CSR neighbour
 *order* — is canonical instead of Delaunator-faithful: every triangle is rotated so its smallest vertex id comes
 first, triangles are sorted lexicographically and oriented counter-clockwise seen from outside; the SphereMesh
-constructor logic (js/sphere-mesh.js:102-145) is then applied unchanged.  **Parity unpinned**: no reference vectors
-exist for this stage.
+constructor logic (js/sphere-mesh.js:102-145) is then applied unchanged.  The canonical numbering is this repository's own
+(there is nothing in the reference to pin it against); the reference-ordered mesh is oracle/delaunator_ref.py.
 """
 from __future__ import annotations
 

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Parity unpinned (no reference vectors exist).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see js_semantics.h).  Pinned against the reference's own source run under tests/golden/minijs.py (tests/test_zz_reference_vectors.py).
 // Sequential restatement of the plate pipeline on the hi-res mesh:
 //   projectCoarsePlates        js/coarse-plates.js:51-117
 //   smoothAndReconnectPlates   js/plates.js:241-348

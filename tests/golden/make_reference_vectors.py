@@ -10,7 +10,7 @@ Two things the reference pulls from outside its tree are supplied by the host, a
   * `delaunator@5.0.1` (CDN import, js/planet-worker.js:17) → oracle/delaunator_ref.py, a restatement of the published
     algorithm.  Every array downstream of the mesh depends only on the reference's code GIVEN that triangulation;
   * `Math.sin/cos/exp/pow/…` → Python's libm (V8 uses an fdlibm port; include/pb_detmath.h is a third implementation).
-tests/test_reference_vectors.py compares the oracle, the host emulation and (under -m gpu) the CUDA library with these files.
+tests/test_zz_reference_vectors.py compares the oracle, the host emulation and (under -m gpu) the CUDA library with these files.
 """
 from __future__ import annotations
 
@@ -49,11 +49,16 @@ SCENARIOS = {
     "D_import_600": [
         dict(cmd="importHeightmap", N=600, jitter=0.75, IMAGE=(64, 32), seed=11, **SLIDERS),
     ],
+    "G_200500": [     # above 200 000 regions assignElevation / findCollisions switch to 2 noise octaves (js/elevation.js:55, 457)
+        dict(cmd="generate", N=200500, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, skipClimate=True, **SLIDERS),
+    ],
     "E_single_layer_400": [     # P < 8: no super plates (js/planet-worker.js:207), single-layer collisions
         dict(cmd="generate", N=400, P=6, jitter=0.75, nMag=0.4, numContinents=2, continentSizeVariety=0.0, seed=3, **SLIDERS),
     ],
 }
-# C keeps only the arrays BASELINE's configs name (the rest can be regenerated); the others keep every array of every reply
+# C keeps only the arrays BASELINE's configs name (the rest can be regenerated), G three full arrays plus SHA-256 digests of the
+# others (fixture size); the other scenarios keep every array of every reply
+KEEP_G = {"r_plate", "prePostElev", "r_elevation"}
 KEEP_C = {"r_plate", "prePostElev", "r_elevation", "r_stress", "t_elevation", "r_wind_east_summer", "r_wind_north_winter",
           "r_ocean_warmth_summer", "r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter",
           "debugLayers.erosionDelta", "debugLayers.koppen", "debugLayers.hotspot", "debugLayers.superPlates"}
@@ -142,6 +147,10 @@ def run_scenario(name):
         arrays, meta = flatten(reply)
         if name.startswith("C_"):
             arrays = {k: v for k, v in arrays.items() if k in KEEP_C}
+        if name.startswith("G_"):
+            import hashlib
+            meta["sha256"] = {k: hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() for k, v in arrays.items()}
+            arrays = {k: v for k, v in arrays.items() if k in KEEP_G}
         for k, v in arrays.items():
             out[f"{i}/{k}"] = v
         metas.append(meta)
@@ -213,7 +222,7 @@ _LAST = {}
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE_JS):
         sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
-    names = sys.argv[1:] or list(SCENARIOS) + ["F_render_600"]
+    names = sys.argv[1:] or [n for n in SCENARIOS if n != "G_200500"] + ["F_render_600"]      # G takes about an hour: ask for it by name
     for n in names:
         print(n, flush=True)
         if n == "F_render_600":

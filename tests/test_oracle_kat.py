@@ -1,5 +1,7 @@
 """Pins the oracle against the derived known-answer vectors of SURVEY.md §8(c).  The reference ships
-no tests or golden vectors and no JS runtime exists here ("parity unpinned" by the reference)."""
+no tests or golden vectors and no JS runtime exists here; these vectors were derived by hand from the cited lines.  (Since
+round 2 the reference's own rng.js / simplex-noise.js reproduce them under tests/golden/minijs.py, and whole worker replies
+are pinned in tests/test_zz_reference_vectors.py.)"""
 import numpy as np
 
 
