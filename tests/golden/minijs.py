@@ -667,6 +667,14 @@ def get_prop(obj, key, line=None):
         if k == "bind":
             return HostFunction(lambda this, args: HostFunction(lambda t2, a2: call_function(obj, args[0] if args else UNDEF, list(args[1:]) + list(a2)), "bound"), "bind")
         return UNDEF
+    if t is _PyIter:
+        if key == "next":
+            def nxt(this, args):
+                for v in obj.it:
+                    return JSObject(None, {"value": v, "done": False})
+                return JSObject(None, {"value": UNDEF, "done": True})
+            return HostFunction(nxt, "next")
+        return UNDEF
     if t is ArrayBuffer:
         if key == "byteLength":
             return float(len(obj.arr) * obj.arr.itemsize)
@@ -810,7 +818,7 @@ class _PyIter:
     __slots__ = ("it",)
 
     def __init__(self, it):
-        self.it = it
+        self.it = iter(it)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

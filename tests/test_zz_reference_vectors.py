@@ -22,7 +22,7 @@ import pytest
 from planet_heightmap_generation_b200.worker import PlanetWorker
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SCENARIOS = ["A_600", "B_2500", "C_10000", "D_import_600", "E_single_layer_400"]
+SCENARIOS = ["A_600", "B_2500", "C_10000", "D_import_600", "E_single_layer_400", "G_200500"]
 SET_KEYS = ("mountain_r", "coastline_r", "ocean_r")
 REL_TOL = 1e-4            # BASELINE north_star: "float elevation/climate within 1e-4 relative"
 MAX_ULP_FLIPS = 2         # Float32 elements per array allowed to differ at all (see the module docstring)
@@ -101,6 +101,15 @@ def check_reply(name, i, reply, rmeta, arrays, stats):
     for key in ("numRegions", "seed", "nMag", "skipClimate"):
         if key in rmeta:
             assert reply[key] == rmeta[key], key
+    # the 200 501-cell scenario stores three arrays in full and SHA-256 digests of all of them
+    import hashlib
+    for key, digest in (rmeta.get("sha256") or {}).items():
+        v = lookup(reply, key)
+        assert v is not None, key
+        got = hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest()
+        if got != digest and key not in arrays:
+            raise AssertionError(f"{name}[{i}].{key}: SHA-256 differs from the reference's array")
+        stats["sha_checked"] = stats.get("sha_checked", 0) + 1
 
 
 def test_vectors_are_complete():
