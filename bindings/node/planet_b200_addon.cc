@@ -273,6 +273,26 @@ napi_value SmoothField(napi_env env, napi_callback_info info) {
     return undefined(env);
 }
 
+// getMeshTriangles() → {triangles:Int32Array, halfedges:Int32Array}: SphereMesh.triangles / .halfedges of the retained mesh
+// (js/sphere-mesh.js:94-100; the worker posts both in its `done` reply and reads s_begin_r(s) = triangles[s])
+napi_value GetMeshTriangles(napi_env env, napi_callback_info info) {
+    NEED_MESH(env);
+    const size_t n3 = 3 * (size_t)pb_mesh_num_triangles(g_mesh);
+    void *t, *h;
+    napi_value tt = new_typed(env, napi_int32_array, n3, 4, &t), th = new_typed(env, napi_int32_array, n3, 4, &h);
+    PB_TRY(env, pb_mesh_get_triangles(g_mesh, static_cast<int32_t*>(t), static_cast<int32_t*>(h)));
+    napi_value out; napi_create_object(env, &out);
+    napi_set_named_property(env, out, "triangles", tt); napi_set_named_property(env, out, "halfedges", th);
+    return out;
+}
+// generateTriangleCenters(mesh, r_xyz) → Float32Array                              js/sphere-mesh.js:206
+napi_value GenerateTriangleCenters(napi_env env, napi_callback_info info) {
+    NEED_MESH(env);
+    void* d; napi_value out = new_typed(env, napi_float32_array, 3 * (size_t)pb_mesh_num_triangles(g_mesh), 4, &d);
+    PB_TRY(env, pb_generate_triangle_centers(g_mesh, static_cast<float*>(d)));
+    return out;
+}
+
 // exportMapPixels(type, width, r_elevation, r_koppen | null) → Uint8ClampedArray(width * width/2 * 4): the ImageData of exportMap
 // (js/planet-mesh.js:1752-1950) — `new ImageData(pixels, width)` + putImageData + canvas.toBlob stay on the JS side
 napi_value ExportMapPixels(napi_env env, napi_callback_info info) {
@@ -410,6 +430,8 @@ NAPI_MODULE_INIT() {
         {"classifyKoppenFlat", nullptr, ClassifyKoppen, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"getClimateField", nullptr, GetClimateField, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"smoothField", nullptr, SmoothField, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"getMeshTriangles", nullptr, GetMeshTriangles, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"generateTriangleCenters", nullptr, GenerateTriangleCenters, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"exportMapPixels", nullptr, ExportMapPixels, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"buildSphereFlat", nullptr, BuildSphere, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"generateCoarsePlatesFlat", nullptr, GenerateCoarsePlates, nullptr, nullptr, nullptr, napi_default, nullptr},

@@ -4,9 +4,13 @@
 //   - import { warpTerrain, smoothElevation, erodeComposite, sharpenRidges, applySoilCreep } from './terrain-post.js';
 //   - import { assignElevation } from './elevation.js';
 //   - import { computeWind } from './wind.js';  import { computeOceanCurrents } from './ocean.js';  …
-//   + import * as gpu from '../bindings/node/planet_worker_shim.mjs';   // then gpu.setMesh(mesh, r_xyz) after buildSphere (:149)
+//   + import { warpTerrain, …, assignElevation, computeWind, … } from '../bindings/node/planet_worker_shim.mjs';
 //
-// (Node worker_threads build of the worker; the browser build keeps the JS modules.)  Not runnable in this image.
+// Every name js/planet-worker.js imports (:4-17) is exported here, so the swap is the import lines and nothing else: makeRng and
+// SimplexNoise come from here too (they carry the seed the library needs), buildSphere returns a mesh object with the SphereMesh
+// members the handlers read.  (Node worker_threads build of the worker; the browser build keeps the JS modules.)  No Node exists
+// in this image: tests/test_zz_dropin_worker.py executes the unmodified reference worker over THIS file with the import lines
+// redirected, under the evaluator tests/golden/minijs.py and the in-process Node-API runtime tests/napi_host/.
 import { createRequire } from 'node:module';
 const native = createRequire(import.meta.url)('./build/Release/planet_b200_addon.node');
 
@@ -20,12 +24,46 @@ export const sharpenRidges = native.sharpenRidges;
 export const applySoilCreep = native.applySoilCreep;
 export const smoothField = native.smoothField;
 
-// buildSphere(N, jitter, rng): the addon needs the seed the caller's rng was built from — pass {seed} (makeRng(seed), :146).
-// Returns {mesh, r_xyz} like js/sphere-mesh.js:174; the mesh is also retained for the stage functions below.
+// What the worker builds itself and hands to the stage functions only as a carrier of its seed (js/planet-worker.js:146, 203):
+// makeRng(seed) and new SimplexNoise(seed).  Imported from here they remember the seed; the streams themselves run in the library.
+export function makeRng(seed) {          // js/rng.js:3-6 (Park–Miller on a hashed seed); the worker itself draws the plate densities from it (:196-199)
+  let state = Math.abs(Math.floor(seed * 9301 + 49297)) % 2147483646 + 1;
+  const rng = () => ((state = state * 16807 % 2147483647) - 1) / 2147483646;
+  rng.seed = seed;
+  return rng;
+}
+export class SimplexNoise { constructor(seed) { this.seed = seed; } }
+export function setDelaunator() {}        // the triangulator is the library's (option mesh_order)
+
+// The members of SphereMesh (js/sphere-mesh.js:94-172) that the worker and the main thread read.
+class RetainedMesh {
+  constructor(r) {
+    const t = native.getMeshTriangles();
+    this.numRegions = r.numRegions; this.adjOffset = this._adjOffset = r.adjOffset; this.adjList = this._adjList = r.adjList;
+    this.triangles = t.triangles; this.halfedges = t.halfedges;
+    this.numSides = t.triangles.length; this.numTriangles = (t.triangles.length / 3) | 0;
+  }
+  _next(s) { return (s % 3 === 2) ? s - 2 : s + 1; }
+  s_begin_r(s) { return this.triangles[s]; }
+  s_end_r(s) { return this.triangles[this._next(s)]; }
+  s_inner_t(s) { return (s / 3) | 0; }
+  s_outer_t(s) { return (this.halfedges[s] / 3) | 0; }
+  r_circulate_r(out, r) {
+    const start = this.adjOffset[r], len = this.adjOffset[r + 1] - start;
+    out.length = len;
+    for (let i = 0; i < len; i++) out[i] = this.adjList[start + i];
+    return out;
+  }
+}
+export { RetainedMesh as SphereMesh };
+
+// buildSphere(N, jitter, rng) with rng = makeRng(seed) from this module.  Returns {mesh, r_xyz} like js/sphere-mesh.js:174; the
+// mesh is also retained for the stage functions below.
 export function buildSphere(N, jitter, rng) {
   const r = native.buildSphereFlat(N, jitter, rng.seed);
-  return { mesh: { numRegions: r.numRegions, adjOffset: r.adjOffset, adjList: r.adjList }, r_xyz: r.r_xyz };
+  return { mesh: new RetainedMesh(r), r_xyz: r.r_xyz };
 }
+export function generateTriangleCenters(mesh, r_xyz) { return native.generateTriangleCenters(); }
 
 // generateCoarsePlates(seed, numPlates, numContinents, continentSizeVariety, landCoverage)      js/coarse-plates.js:19
 export function generateCoarsePlates(seed, numPlates, numContinents, continentSizeVariety = 0, landCoverage = 0.3) {

@@ -64,6 +64,18 @@ class JSObject:
         self.cls = None
 
 
+class JSProxy:
+    """new Proxy(target, {get, has, ownKeys}) — the three traps bindings/node/planet_worker_shim.mjs uses"""
+    __slots__ = ("target", "handler")
+
+    def __init__(self, target, handler):
+        self.target, self.handler = target, handler
+
+    def trap(self, name):
+        f = self.handler.props.get(name)
+        return f if f is not None and f is not UNDEF else None
+
+
 class Accessor:
     __slots__ = ("get", "set")
 
@@ -667,6 +679,10 @@ def get_prop(obj, key, line=None):
         if k == "bind":
             return HostFunction(lambda this, args: HostFunction(lambda t2, a2: call_function(obj, args[0] if args else UNDEF, list(args[1:]) + list(a2)), "bound"), "bind")
         return UNDEF
+    if t is JSProxy:
+        f = obj.trap("get")
+        k = key if type(key) is str else to_str(key)
+        return call_function(f, obj.handler, [obj.target, k, obj]) if f else get_prop(obj.target, k)
     if t is _PyIter:
         if key == "next":
             def nxt(this, args):
@@ -733,6 +749,9 @@ def set_prop(obj, key, value):
         return
     if t is JSFunction or t is HostFunction:
         obj.props[prop_key(key)] = value
+        return
+    if t is JSProxy:
+        set_prop(obj.target, key, value)
         return
     throw_error("TypeError", f"Cannot set properties of {to_display(obj)} (setting '{to_display(key)}')")
 
@@ -934,6 +953,7 @@ ARRAY_METHODS = {
     "findIndex": lambda a, args: next((float(i) for i, x in enumerate(list(a)) if truthy(call_function(args[0], UNDEF, [x, float(i), a]))), -1.0),
     "reduce": _reduce,
     "flat": lambda a, args: _flat(a, int(to_num(_arg(args, 0, 1.0)))),
+    "flatMap": lambda a, args: _flat(JSArray([call_function(args[0], UNDEF, [x, float(i), a]) for i, x in enumerate(list(a))]), 1),
     "keys": lambda a, args: _PyIter(float(i) for i in range(len(a))),
     "values": lambda a, args: _PyIter(iterate(a)),
     "entries": lambda a, args: _PyIter(JSArray([float(i), x]) for i, x in enumerate(list(a))),
@@ -1319,6 +1339,10 @@ def _object_assign(this, args):
 
 
 def _entries_of(o):
+    if type(o) is JSProxy:
+        f = o.trap("ownKeys")
+        keys = [to_str(k) for k in iterate(call_function(f, o.handler, [o.target]))] if f else [k for k, _ in _entries_of(o.target)]
+        return [(k, get_prop(o, k)) for k in keys]
     if type(o) is JSObject:
         return [(k, get_prop(o, k)) for k in own_keys(o)]
     if type(o) is JSArray:
@@ -1440,6 +1464,12 @@ def make_globals(log=None, random_fn=None):
     g["Date"] = JSObject(None, {"now": HostFunction(lambda this, args: float(int(time.time() * 1000)), "now")})
     g["JSON"] = JSObject(None, {"stringify": HostFunction(lambda this, args: _json_value(_arg(args, 0)), "stringify")})
     g["globalThis"] = JSObject()
+
+    def proxy_ctor(args):
+        if type(_arg(args, 0)) is not JSObject or type(_arg(args, 1)) is not JSObject:
+            throw_error("TypeError", "Cannot create proxy with a non-object as target or handler")
+        return JSProxy(args[0], args[1])
+    g["Proxy"] = HostFunction(lambda this, args: throw_error("TypeError", "Constructor Proxy requires 'new'"), "Proxy", proxy_ctor)
     return g
 
 
@@ -2407,6 +2437,11 @@ class Compiler:
                     i = index_of(key)
                     n = len(o) if type(o) is JSArray else o.length
                     return 0 <= i < n or key == "length"
+                if type(o) is JSProxy:
+                    f = o.trap("has")
+                    if f:
+                        return truthy(call_function(f, o.handler, [o.target, prop_key(key)]))
+                    return prop_key(key) in o.target.props
                 throw_error("TypeError", "Cannot use 'in' operator on a primitive")
             return in_
         if op == "instanceof":
@@ -2687,6 +2722,10 @@ class Compiler:
         argsf = self.args(args, scope)
         return lambda env: construct(ff(env), argsf(env), line)
 
+    def e_importmeta(self, e, scope):
+        url = "file://" + self.fname
+        return lambda env: JSObject(None, {"url": url})
+
     def e_spread(self, e, scope):
         raise NotImplementedError("spread outside of a call / array / object literal")
 
@@ -2709,8 +2748,11 @@ class Module:
 
 
 class Interpreter:
-    def __init__(self, root: str, host_modules=None, random_fn=None):
+    def __init__(self, root: str, host_modules=None, random_fn=None, import_map=None):
+        """import_map: {(basename of the importing file, specifier): replacement path} — swaps a module's imports without
+        touching its source (the drop-in test loads the reference worker over bindings/node/planet_worker_shim.mjs this way)"""
         self.root = root
+        self.import_map = import_map or {}
         self.console = []
         self.globals = make_globals(self.console, random_fn)
         self.modules = {}
@@ -2741,6 +2783,7 @@ class Interpreter:
         # imports: evaluate dependencies first, then copy the bindings (the reference has no `export let` that is reassigned)
         for s in imports:
             spec = s[2]
+            spec = self.import_map.get((os.path.basename(path), spec), spec)
             if spec in self.host_modules:
                 exports = self.host_modules[spec]
                 getter = exports.get

@@ -347,7 +347,7 @@ class Parser:
                         body.append(self.statement())
                     cases.append((test, body))
                 return ("switch", disc, cases)
-            if v == "import":
+            if v == "import" and not (self.peek().kind == "punct" and self.peek().val == "."):
                 return self.import_decl()
             if v == "export":
                 return self.export_decl()
@@ -833,6 +833,11 @@ class Parser:
             if v == "super":
                 self.i += 1
                 return ("super",)
+            if v == "import" and self.peek().kind == "punct" and self.peek().val == ".":
+                self.i += 2
+                if self.prop_name() != "meta":
+                    self.err("only import.meta is supported")
+                return ("importmeta",)
             if v in CONTEXTUAL:
                 self.i += 1
                 return ("id", v)
