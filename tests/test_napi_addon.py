@@ -29,7 +29,7 @@ def test_addon_exports(addon):
     want = {"setMesh", "setOption", "computeNeighborDist", "warpTerrain", "smoothElevation", "erodeComposite", "sharpenRidges",
             "applySoilCreep", "runPostProcessing", "assignElevationFlat", "computeWindFlat", "computeOceanCurrentsFlat",
             "computePrecipitationFlat", "computeTemperatureFlat", "classifyKoppenFlat", "getClimateField", "smoothField",
-            "exportMapPixels", "buildSphereFlat", "generateCoarsePlatesFlat", "projectCoarsePlatesFlat",
+            "exportMapPixels", "getMeshTriangles", "generateTriangleCenters", "buildSphereFlat", "generateCoarsePlatesFlat", "projectCoarsePlatesFlat",
             "smoothAndReconnectPlatesFlat", "buildSuperPlatesFlat"}
     assert set(addon.exports) == want
 
@@ -47,6 +47,10 @@ def test_addon_generate_chain_matches_oracle(addon, oracle):
     assert_bit_equal(s["adjList"], mesh.adjList, "adjList")
     nd = addon.computeNeighborDist()
     assert_bit_equal(nd, oracle.neighbor_dist(mesh, xyz), "neighborDist")
+    tri = addon.getMeshTriangles()
+    assert_bit_equal(tri["triangles"], mesh.triangles, "triangles")
+    assert_bit_equal(tri["halfedges"], mesh.halfedges, "halfedges")
+    assert_bit_equal(addon.generateTriangleCenters(), oracle.triangle_centers(mesh, xyz), "t_xyz")
 
     # generateCoarsePlates → projectCoarsePlates → smoothAndReconnectPlates (:160-173)
     cp = addon.generateCoarsePlatesFlat(SEED, P, CONT, 0.0, 0.3)
