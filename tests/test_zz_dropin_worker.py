@@ -2,7 +2,8 @@
 handleComputeClimate, handleEditRecompute, its private runPostProcessing / computeTriangleElevations / buildClimateFields) runs with
 its import lines redirected to bindings/node/planet_worker_shim.mjs, which forwards every stage function to the Node-API addon
 (bindings/node/planet_b200_addon.cc) and through it to the C ABI.  Nothing of the reference's compute modules is loaded; the
-replies must equal the ones the all-JavaScript reference worker produced (tests/golden/reference_A_600.npz) bit for bit.
+replies must equal the ones the all-JavaScript reference worker produced (tests/golden/reference_*.npz: generate, reapply,
+computeClimate, editRecompute, importHeightmap, single- and dual-layer planets) bit for bit.
 
 No Node and no JavaScript runtime exist in this image: the JavaScript (worker + shim) is evaluated by tests/golden/minijs.py, the
 addon by the in-process Node-API runtime tests/napi_host/.  Needs the reference tree, so it only runs in the build container."""
@@ -57,7 +58,8 @@ def _native_module(addon):
     return {"createRequire": js.HostFunction(lambda this, args: require, "createRequire")}
 
 
-def test_reference_worker_over_the_shim_reproduces_its_own_replies():
+@pytest.mark.parametrize("name", ["A_600", "D_import_600", "E_single_layer_400", "B_2500"])
+def test_reference_worker_over_the_shim_reproduces_its_own_replies(name):
     from tests.emul.build_emul import build
     from tests.golden import minijs as js
     from tests.napi_host.host import NapiHost
@@ -75,7 +77,7 @@ def test_reference_worker_over_the_shim_reproduces_its_own_replies():
     loaded = {os.path.basename(p) for p in it.modules}
     assert loaded == {"planet-worker.js", "planet_worker_shim.mjs"}, f"a compute module of the reference was loaded: {loaded}"
 
-    commands, replies = load("A_600")
+    commands, replies = load(name)
     stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
     for i, (cmd, (rmeta, arrays)) in enumerate(zip(commands, replies)):
         del posted[:]
@@ -89,5 +91,5 @@ def test_reference_worker_over_the_shim_reproduces_its_own_replies():
         for key in ("plateDensity", "plateDensityLand", "plateDensityOcean", "plateVec"):
             if isinstance(reply.get(key), dict):
                 reply[key] = {int(k): v for k, v in reply[key].items()}
-        check_reply("dropin A_600", i, reply, rmeta, arrays, stats)
-    assert stats["float_differing"] == 0 and stats["float_elements"] > 70000
+        check_reply("dropin " + name, i, reply, rmeta, arrays, stats)
+    assert stats["float_differing"] == 0 and stats["float_elements"] > 20000
