@@ -87,15 +87,27 @@ def main():
                    landCoverage=float(rng.choice([0.05, 0.15, 0.3, 0.5, 0.85])), seed=int(rng.integers(0, 16777216)), **sliders())
         if rng.random() < 0.3:
             gen["toggledIndices"] = [int(rng.integers(0, gen["P"]))]
+        imported = os.environ.get("FUZZ_IMPORT") == "1" or rng.random() < 0.15
+        if imported:          # importHeightmap (js/planet-worker.js:771-942) of a random smooth image with black oceans
+            iw = int(rng.choice([32, 64, 100]))
+            ih = iw // 2
+            yy, xx = np.mgrid[0:ih, 0:iw]
+            img = 120 + 80 * np.sin(xx * rng.uniform(0.1, 0.5) + rng.uniform(0, 6)) * np.cos(yy * rng.uniform(0.1, 0.6)) + 30 * rng.random((ih, iw))
+            img[np.sin(xx * rng.uniform(0.05, 0.3) + yy * rng.uniform(0.05, 0.3)) > rng.uniform(-0.3, 0.5)] = 0
+            gen = dict(cmd="importHeightmap", N=gen["N"], jitter=gen["jitter"], grayscale=np.clip(np.round(img), 0, 255).astype(np.uint8).ravel(),
+                       imageWidth=iw, imageHeight=ih, seed=gen["seed"], temperatureOffset=gen["temperatureOffset"],
+                       precipitationOffset=gen["precipitationOffset"], **{k: gen[k] for k in SLIDER_KEYS})
         t0 = time.time()
 
-        def commands_fn(ref, case=first + k):
+        def commands_fn(ref, case=first + k, gen=gen):
             r2 = np.random.default_rng(7 + case)          # the follow-up commands are a function of the case number: both replays get the same
             sl = lambda: {s: float(r2.choice([0.0, 1.0, np.round(r2.random(), 2)], p=[0.15, 0.15, 0.7])) for s in SLIDER_KEYS}   # noqa: E731
             seeds = [int(s) for s in ref["plateSeeds"]]
             ocean = {int(s) for s in ref["plateIsOcean"]} ^ {seeds[int(r2.integers(0, len(seeds)))]}
             dens = {int(kk): float(v) for kk, v in ref["plateDensity"].items()}
             dens[seeds[0]] = float(np.round(2.4 + r2.random(), 3))
+            if ref.get("type") == "done" and gen["cmd"] == "importHeightmap":
+                return [dict(cmd="reapply", skipClimate=bool(r2.random() < 0.5), **sl()), dict(cmd="computeClimate", temperatureOffset=1.5, precipitationOffset=0.1)]
             return [dict(cmd="reapply", skipClimate=bool(r2.random() < 0.5), **sl()),
                     dict(cmd="editRecompute", plateIsOcean=sorted(ocean), plateDensity=dens, nMag=float(np.round(r2.random() * 0.6, 2)), **sl()),
                     dict(cmd="computeClimate", temperatureOffset=1.5, precipitationOffset=0.1)]
@@ -120,7 +132,7 @@ def main():
         for kk in ("float_elements", "float_differing", "int_elements"):
             totals[kk] += stats[kk]
         totals["worst"] = max(totals["worst"], stats["worst"])
-        print(f"round {first + k}: N={gen['N']} P={gen['P']} cont={gen['numContinents']} var={gen['continentSizeVariety']} land={gen['landCoverage']} "
+        print(f"round {first + k}: {gen['cmd']} N={gen['N']} P={gen.get('P')} cont={gen.get('numContinents')} var={gen.get('continentSizeVariety')} land={gen.get('landCoverage')} "
               f"jitter={gen['jitter']} seed={gen['seed']} toggled={gen.get('toggledIndices')} floats={stats['float_elements']} "
               f"differing={stats['float_differing']} ints={stats['int_elements']} [{time.time() - t0:.0f} s] -> {verdict}", flush=True)
     print(f"rounds {rounds}, failures {bad}, last-bit-only {lastbit}, totals (libm runs) {totals}")
