@@ -52,6 +52,9 @@ SCENARIOS = {
     "G_200500": [     # above 200 000 regions assignElevation / findCollisions switch to 2 noise octaves (js/elevation.js:55, 457)
         dict(cmd="generate", N=200500, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, skipClimate=True, **SLIDERS),
     ],
+    "H_1000000": [    # the benchmark planet itself (bench.py: 1 000 001 cells, seed 42, slider defaults), climate skipped; ≈ 1.5 h
+        dict(cmd="generate", N=1000000, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, skipClimate=True, **SLIDERS),
+    ],
     "E_single_layer_400": [     # P < 8: no super plates (js/planet-worker.js:207), single-layer collisions
         dict(cmd="generate", N=400, P=6, jitter=0.75, nMag=0.4, numContinents=2, continentSizeVariety=0.0, seed=3, **SLIDERS),
     ],
@@ -151,6 +154,14 @@ def run_scenario(name):
             import hashlib
             meta["sha256"] = {k: hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() for k, v in arrays.items()}
             arrays = {k: v for k, v in arrays.items() if k in KEEP_G}
+        if name.startswith("H_"):
+            # 1M cells: no array is stored; per array one 8-byte digest per block of 4096 elements (a difference is localised to blocks)
+            import hashlib
+            blocks = {}
+            for k, v in arrays.items():
+                b = np.ascontiguousarray(v)
+                blocks[k] = np.frombuffer(b"".join(hashlib.sha256(b[i:i + 4096].tobytes()).digest()[:8] for i in range(0, b.size, 4096)), np.uint8)
+            arrays = {"blocks." + k: v for k, v in blocks.items()}
         for k, v in arrays.items():
             out[f"{i}/{k}"] = v
         metas.append(meta)
@@ -222,7 +233,7 @@ _LAST = {}
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE_JS):
         sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
-    names = sys.argv[1:] or [n for n in SCENARIOS if n != "G_200500"] + ["F_render_600"]      # G takes about an hour: ask for it by name
+    names = sys.argv[1:] or [n for n in SCENARIOS if n[0] not in "GH"] + ["F_render_600"]      # G ≈ 15 min, H ≈ 1.5 h: ask for them by name
     for n in names:
         print(n, flush=True)
         if n == "F_render_600":
