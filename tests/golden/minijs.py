@@ -1142,16 +1142,15 @@ def _math1(fn, domain_nan=True):
 
 
 def _math_round(this, args):
+    """round half toward +Infinity; floor(x + 0.5) would be wrong for 0.49999999999999994 and above 2^52"""
     x = to_num(_arg(args, 0))
-    if x != x or x in (INF, -INF):
+    if x != x or x in (INF, -INF) or abs(x) >= 4503599627370496.0:
         return x
-    r = math.floor(x + 0.5)
+    f = math.floor(x)
+    r = float(f + 1 if x - f >= 0.5 else f)          # x - floor(x) is exact below 2^52
     if r == 0 and (x < 0 or math.copysign(1.0, x) < 0):
         return -0.0
-    # x + 0.5 may round up for the largest doubles below an integer boundary (0.49999999999999994): JS rounds those down
-    if x + 0.5 - 1.0 == x - 0.5 and float(r) - x > 0.5:
-        r -= 1
-    return float(r)
+    return r
 
 
 def _math_floor(this, args):
