@@ -227,16 +227,58 @@ def run_render_scenario():
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out)} arrays)")
 
 
+def run_stage_scenario():
+    """I_post50_2500: the five exported stage functions of js/terrain-post.js called one by one on scenario B's planet with
+    BASELINE config 2's parameters — hIters = 50 passed directly (the sliders only reach 20), K = 0.0003, m = 0.5, dt = 1,
+    tIters = 1, gIters = 5 — which puts the second priority flood at iteration 38 (:446).  Plus smoothField and percentile of
+    js/climate-util.js.  The elevation after every stage is stored."""
+    from tests.golden import minijs as js
+    post = make_interpreter()
+    reply = post(dict(SCENARIOS["B_2500"][0]))
+    interp = _LAST["interp"]
+    worker = interp.modules[os.path.realpath(os.path.join(REFERENCE_JS, "planet-worker.js"))]
+    W = worker.env.v["W"]
+    mesh, r_xyz, nd = js.get_prop(W, "mesh"), js.get_prop(W, "r_xyz"), js.get_prop(W, "neighborDist")
+    tp = lambda n: interp.get_export("terrain-post.js", n)          # noqa: E731
+    elev = js.from_python(reply["prePostElev"].copy())
+    hot = js.from_python(reply["debugLayers"]["hotspot"])
+    out = {"in.prePostElev": reply["prePostElev"], "in.hotspot": reply["debugLayers"]["hotspot"], "in.triangles": reply["triangles"],
+           "in.halfedges": reply["halfedges"], "in.r_xyz": reply["r_xyz"]}
+    t0 = time.time()
+    js.call_function(tp("warpTerrain"), js.UNDEF, [mesh, elev, r_xyz, 7.0, 0.75, hot])
+    out["1.warpTerrain"] = js.to_python(elev)
+    is_ocean = js.from_python((out["1.warpTerrain"] <= 0).astype(np.uint8))
+    js.call_function(tp("smoothElevation"), js.UNDEF, [mesh, elev, is_ocean, 1.0, 0.25])
+    out["2.smoothElevation"] = js.to_python(elev)
+    js.call_function(tp("erodeComposite"), js.UNDEF, [mesh, elev, r_xyz, is_ocean, 50.0, 0.0003, 0.5, 1.0, 1.0, 1.16, 0.015, 5.0, 0.5, nd])
+    out["3.erodeComposite"] = js.to_python(elev)
+    js.call_function(tp("sharpenRidges"), js.UNDEF, [mesh, elev, is_ocean, 3.0, 0.04])
+    out["4.sharpenRidges"] = js.to_python(elev)
+    js.call_function(tp("applySoilCreep"), js.UNDEF, [mesh, elev, is_ocean, 3.0, 0.1125])
+    out["5.applySoilCreep"] = js.to_python(elev)
+    field = js.from_python(reply["r_precip_summer"].copy())
+    js.call_function(interp.get_export("climate-util.js", "smoothField"), js.UNDEF, [mesh, field, 7.0])
+    out["6.smoothField7"] = js.to_python(field)
+    out["7.percentiles"] = np.asarray([js.call_function(interp.get_export("climate-util.js", "percentile"), js.UNDEF,
+                                                        [js.from_python(reply["r_elevation"]), p]) for p in (0.0, 0.05, 0.5, 0.95, 0.97, 0.999)], np.float64)
+    print(f"  stage functions in {time.time() - t0:.0f} s")
+    path = os.path.join(HERE, "reference_I_post50_2500.npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out)} arrays)")
+
+
 _LAST = {}
 
 
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE_JS):
         sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
-    names = sys.argv[1:] or [n for n in SCENARIOS if n[0] not in "GH"] + ["F_render_600"]      # G ≈ 15 min, H ≈ 1.5 h: ask for them by name
+    names = sys.argv[1:] or [n for n in SCENARIOS if n[0] not in "GH"] + ["F_render_600", "I_post50_2500"]      # G ≈ 15 min, H ≈ 1.5 h: ask for them by name
     for n in names:
         print(n, flush=True)
         if n == "F_render_600":
             run_render_scenario()
+        elif n == "I_post50_2500":
+            run_stage_scenario()
         else:
             run_scenario(n)
