@@ -5,6 +5,8 @@ generate → reapply → editRecompute → computeClimate to the unmodified refe
 the engine's worker mirror (host emulation of the kernels, reference neighbour order), and compares every array of every reply
 with the criteria of tests/test_zz_reference_vectors.py (integers identical; Float32 identical up to two last-bit flips per array
 and 1e-4 relative).  Usage:  python tests/golden/fuzz_reference.py [rounds] [first_seed]
+Environment: FUZZ_NMIN / FUZZ_NMAX (cells), FUZZ_IMPORT=1 (importHeightmap rounds only), FUZZ_MATH=detmath (the evaluator's Math.* is
+include/pb_detmath.h from the start: every Float32 value must then be identical).
 """
 import os
 import sys
@@ -113,7 +115,7 @@ def main():
                     dict(cmd="computeClimate", temperatureOffset=1.5, precipitationOffset=0.1)]
         stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
         try:
-            replay(gen, commands_fn, lib, False, stats)
+            replay(gen, commands_fn, lib, os.environ.get("FUZZ_MATH") == "detmath", stats)
             verdict = "ok"
         except AssertionError as e:
             # same planet with pb_detmath inside the evaluator: a difference that disappears is the elementary functions' last bit
