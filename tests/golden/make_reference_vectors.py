@@ -55,6 +55,9 @@ SCENARIOS = {
     "H_1000000": [    # the benchmark planet itself (bench.py: 1 000 001 cells, seed 42, slider defaults), climate skipped; ≈ 1.5 h
         dict(cmd="generate", N=1000000, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, skipClimate=True, **SLIDERS),
     ],
+    "J_100000": [     # full pipeline incl. the climate stack at 100 001 cells (≈ 300 graph sweeps per field family), block digests; ≈ 25 min
+        dict(cmd="generate", N=100000, P=80, jitter=0.75, nMag=0.4, numContinents=4, continentSizeVariety=0.0, seed=42, **SLIDERS),
+    ],
     "E_single_layer_400": [     # P < 8: no super plates (js/planet-worker.js:207), single-layer collisions
         dict(cmd="generate", N=400, P=6, jitter=0.75, nMag=0.4, numContinents=2, continentSizeVariety=0.0, seed=3, **SLIDERS),
     ],
@@ -154,7 +157,7 @@ def run_scenario(name):
             import hashlib
             meta["sha256"] = {k: hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() for k, v in arrays.items()}
             arrays = {k: v for k, v in arrays.items() if k in KEEP_G}
-        if name.startswith("H_"):
+        if name[0] in "HJ":
             # 1M cells: no array is stored; per array one 8-byte digest per block of 4096 elements (a difference is localised to blocks)
             import hashlib
             blocks = {}
@@ -273,7 +276,7 @@ _LAST = {}
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE_JS):
         sys.exit(f"{REFERENCE_JS} not found: the vectors can only be regenerated where the reference is present")
-    names = sys.argv[1:] or [n for n in SCENARIOS if n[0] not in "GH"] + ["F_render_600", "I_post50_2500"]      # G ≈ 15 min, H ≈ 1.5 h: ask for them by name
+    names = sys.argv[1:] or [n for n in SCENARIOS if n[0] not in "GHJ"] + ["F_render_600", "I_post50_2500"]      # G ≈ 15 min, H ≈ 1.5 h: ask for them by name
     for n in names:
         print(n, flush=True)
         if n == "F_render_600":
