@@ -138,7 +138,7 @@ def test_engine_replays_the_reference_worker(backend, name):
     print(f"{name}: {stats}")
 
 
-@pytest.mark.parametrize("name", ["A_600", "B_2500", "E_single_layer_400"])
+@pytest.mark.parametrize("name", ["A_600", "B_2500", "E_single_layer_400", "J_100000"])
 def test_oracle_replays_the_reference_worker(oracle, name):
     """The oracle's handlers (the checker every other parity test trusts) against the reference's own replies."""
     from tests.test_worker import OracleWorker
@@ -156,8 +156,18 @@ def test_oracle_replays_the_reference_worker(oracle, name):
               "itczLatsWinter", "r_ocean_current_east_summer", "r_ocean_current_north_winter", "r_ocean_speed_summer", "r_ocean_speed_winter",
               "r_ocean_warmth_summer", "r_ocean_warmth_winter", "r_precip_summer", "r_precip_winter", "r_temperature_summer", "r_temperature_winter"):
         got[k] = ow.clim.get(k)
-    for k, v in got.items():
-        check_array(f"oracle {name}.{k}", v, ref[k], stats)
+    if name[0] == "J":        # block digests instead of arrays (100 001 cells)
+        import hashlib
+        for k, v in got.items():
+            v = np.ascontiguousarray(v)
+            if k in ("triangles", "halfedges", "r_plate"):
+                v = v.astype(np.int32)
+            d = np.frombuffer(b"".join(hashlib.sha256(v[i:i + 4096].tobytes()).digest()[:8] for i in range(0, v.size, 4096)), np.uint8)
+            assert (d == ref["blocks." + k]).all(), f"oracle {name}.{k}: block digests differ from the reference's array"
+            stats["float_elements"] += v.size
+    else:
+        for k, v in got.items():
+            check_array(f"oracle {name}.{k}", v, ref[k], stats)
     assert [int(s) for s in rmeta["plateSeeds"]] == ow.seeds
     assert sorted(int(s) for s in rmeta["plateIsOcean"]) == sorted(ow.pio)
     assert {int(k): v for k, v in rmeta["plateDensity"].items()} == ow.dens
