@@ -221,12 +221,13 @@ def test_export_triangles_match_the_reference(oracle, etype):
     assert stats["float_differing"] == 0 and stats["float_elements"] > 60000
 
 
-@pytest.mark.parametrize("name", ["H_1000000", "J_100000"])
+@pytest.mark.parametrize("name", ["H_1000000", "H_1000000_detmath", "J_100000"])
 def test_engine_reproduces_the_reference_block_digests(backend, name):
     """Planets too large to store.  H: the planet bench.py times — 1 000 001 cells, seed 42, slider defaults — generated by the
     reference worker with the climate skipped (820 graph sweeps at that size are beyond the evaluator).  J: the whole pipeline
     including the climate stack at 100 001 cells.  Per array one 8-byte digest per block of 4096 elements is stored; every block of
-    every array — integer and Float32 alike — must match, with the one documented exception below."""
+    every array — integer and Float32 alike — must match, with the one documented exception below.  H_1000000_detmath is the same
+    reference run with include/pb_detmath.h behind the evaluator's Math.*: there every one of the 10 027 blocks must match."""
     import hashlib
     path = os.path.join(GOLDEN, f"reference_{name}.npz")
     if not os.path.exists(path):
