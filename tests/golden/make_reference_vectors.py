@@ -130,6 +130,11 @@ def flatten(reply: dict):
 
 def run_scenario(name):
     post = make_interpreter()
+    suffix = ""
+    if os.environ.get("REF_MATH") == "detmath":      # REF_MATH=detmath python … H_1000000 → reference_H_1000000_detmath.npz
+        from tests.golden.fuzz_reference import use_detmath
+        use_detmath()
+        suffix = "_detmath"
     out, metas, commands = {}, [], []
     last_done = None
     for i, cmd in enumerate(SCENARIOS[name]):
@@ -170,7 +175,7 @@ def run_scenario(name):
         metas.append(meta)
         commands.append({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in cmd.items()})
     out["__meta__"] = np.frombuffer(json.dumps({"commands": commands, "replies": metas}, default=lambda o: o.tolist()).encode(), np.uint8)
-    path = os.path.join(HERE, f"reference_{name}.npz")
+    path = os.path.join(HERE, f"reference_{name}{suffix}.npz")
     np.savez_compressed(path, **out)
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KB, {len(out) - 1} arrays)")
 
