@@ -27,7 +27,7 @@ SLIDER_KEYS = ("smoothing", "glacialErosion", "hydraulicErosion", "thermalErosio
 NRANGE = (int(os.environ.get("FUZZ_NMIN", 300)), int(os.environ.get("FUZZ_NMAX", 2500)))
 
 
-def use_detmath():
+def use_detmath(interp=None):
     """replaces Math.exp/log/pow/atan/asin/acos/atan2/sin/cos/tanh of the evaluator just built by include/pb_detmath.h (through the
     oracle library): with the SAME elementary functions on both sides any remaining difference would be algorithmic"""
     import ctypes as C
@@ -44,7 +44,7 @@ def use_detmath():
             lib.orc_detmath(kind, 1, x, y, o)
             return o[0]
         return f
-    m = _LAST["interp"].globals["Math"]
+    m = (interp or _LAST["interp"]).globals["Math"]
     for name, kind in (("exp", 0), ("log", 1), ("pow", 2), ("atan", 3), ("asin", 4), ("atan2", 5), ("sin", 6), ("cos", 7), ("tanh", 8)):
         m.props[name] = js.HostFunction(det(kind), name)
     asin = det(4)

@@ -133,7 +133,7 @@ def run_scenario(name):
     suffix = ""
     if os.environ.get("REF_MATH") == "detmath":      # REF_MATH=detmath python … H_1000000 → reference_H_1000000_detmath.npz
         from tests.golden.fuzz_reference import use_detmath
-        use_detmath()
+        use_detmath(_LAST["interp"])
         suffix = "_detmath"
     out, metas, commands = {}, [], []
     last_done = None
