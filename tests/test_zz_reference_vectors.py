@@ -259,3 +259,53 @@ def test_engine_reproduces_the_reference_block_digests(backend, name):
     allowed = {"H_1000000": {"debugLayers.hotspot": 1}}.get(name, {})
     for arr, (differing, total) in report.items():
         assert differing <= allowed.get(arr, 0), f"{name}.{arr}: {differing} of {total} blocks of 4096 elements differ from the reference's array"
+
+
+def test_stage_functions_with_50_stream_power_iterations(backend, oracle):
+    """js/terrain-post.js's five exported stage functions (:233, 317, 369, 713, 758) called directly by the generator with BASELINE
+    config 2's parameters — hIters = 50 (second priority flood at iteration 38, :446), K 0.0003, m 0.5, dt 1, tIters 1, gIters 5 —
+    plus smoothField / percentile of js/climate-util.js (:5, 103).  Every stage starts from the reference's output of the stage
+    before, in the engine and in the oracle; then the whole chain end to end."""
+    from planet_heightmap_generation_b200 import terrain_post as tp
+    from planet_heightmap_generation_b200.climate_util import smoothField
+    from planet_heightmap_generation_b200.engine import DeviceMesh
+    from planet_heightmap_generation_b200.mesh import SphereMesh
+    z = np.load(os.path.join(GOLDEN, "reference_I_post50_2500.npz"))
+    xyz = z["in.r_xyz"]
+    mesh = SphereMesh(z["in.triangles"], z["in.halfedges"], xyz.size // 3)
+    nd = oracle.neighbor_dist(mesh, xyz)
+    dm = DeviceMesh(mesh, xyz, lib=backend)
+    hot = z["in.hotspot"]
+    is_ocean = (z["1.warpTerrain"] <= 0).astype(np.uint8)
+    stats = dict(float_elements=0, float_differing=0, int_elements=0, worst=0.0)
+    stages = [
+        ("1.warpTerrain", "in.prePostElev", lambda e: tp.warpTerrain(dm, e, xyz, 7, 0.75, hot), lambda e: oracle.warp_terrain(mesh, e, xyz, 7, 0.75, hot)),
+        ("2.smoothElevation", "1.warpTerrain", lambda e: tp.smoothElevation(dm, e, is_ocean, 1, 0.25), lambda e: oracle.smooth_elevation(mesh, e, is_ocean, 1, 0.25)),
+        ("3.erodeComposite", "2.smoothElevation", lambda e: tp.erodeComposite(dm, e, xyz, is_ocean, 50, 0.0003, 0.5, 1, 1, 1.16, 0.015, 5, 0.5, nd),
+         lambda e: oracle.erode_composite(mesh, e, xyz, is_ocean, 50, 0.0003, 0.5, 1, 1, 1.16, 0.015, 5, 0.5, nd)),
+        ("4.sharpenRidges", "3.erodeComposite", lambda e: tp.sharpenRidges(dm, e, is_ocean, 3, 0.04), lambda e: oracle.sharpen_ridges(mesh, e, is_ocean, 3, 0.04)),
+        ("5.applySoilCreep", "4.sharpenRidges", lambda e: tp.applySoilCreep(dm, e, is_ocean, 3, 0.1125), lambda e: oracle.apply_soil_creep(mesh, e, is_ocean, 3, 0.1125)),
+    ]
+    chain_engine, chain_oracle = z["in.prePostElev"].copy(), z["in.prePostElev"].copy()
+    for name, src, engine_fn, oracle_fn in stages:
+        a, b = z[src].copy(), z[src].copy()
+        engine_fn(a)
+        oracle_fn(b)
+        check_array("engine " + name, a, z[name], stats)
+        check_array("oracle " + name, b, z[name], stats)
+        engine_fn(chain_engine)
+        oracle_fn(chain_oracle)
+    check_array("engine chain", chain_engine, z["5.applySoilCreep"], stats)
+    check_array("oracle chain", chain_oracle, z["5.applySoilCreep"], stats)
+    assert (z["3.erodeComposite"] != z["2.smoothElevation"]).mean() > 0.2          # the erosion did something
+    _, replies = load("B_2500")
+    f1, f2 = replies[0][1]["r_precip_summer"].copy(), replies[0][1]["r_precip_summer"].copy()
+    smoothField(dm, f1, 7)
+    oracle.smooth_field(mesh, f2, 7)
+    check_array("engine smoothField", f1, z["6.smoothField7"], stats)
+    check_array("oracle smoothField", f2, z["6.smoothField7"], stats)
+    elev = replies[0][1]["r_elevation"]
+    got = [oracle.percentile(elev, p) for p in (0.0, 0.05, 0.5, 0.95, 0.97, 0.999)]
+    assert got == z["7.percentiles"].tolist()
+    assert stats["float_differing"] == 0
+    dm.close()
