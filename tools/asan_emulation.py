@@ -4,9 +4,12 @@ host-serial stages, C ABI argument handling) is the same code in the CUDA build.
 
   g++ -x c++ -std=c++17 -O1 -g -fPIC -ffp-contract=off -DPB_EMUL -fsanitize=address,undefined -fno-omit-frame-pointer -shared \
       -o /tmp/libpb_hostemu_asan.so planet_heightmap_generation_b200/csrc/planet_b200.cu
-  LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python tools/asan_emulation.py
+  LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libstdc++.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
+      python tools/asan_emulation.py
+(libstdc++ is preloaded as well so that ASan's __cxa_throw interceptor finds the real function when the library raises a C++ exception.)
 
-Last run (end of round 2): clean."""
+Last run (end of round 2): clean; so are the four flows of tests/test_napi_addon.py with napi_host.cc + the addon compiled with the
+same flags against that library (error paths included)."""
 import os
 import sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
